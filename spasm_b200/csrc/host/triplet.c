@@ -109,19 +109,22 @@ struct spasm_csr *spasm_compress(const struct spasm_triplet *T)
 	Cp[n] = out;
 	free(slot);
 
-	/* 3. squeeze out the entries that cancelled */
+	/* 3. squeeze out the entries that cancelled.
+	 * Reference quirk kept on purpose (src/spasm_triplet.c:36-57): the reference compacts in place and
+	 * begins the scan of row i at the already-rewritten row pointer, i.e. at the write cursor, so
+	 * after the first dropped entry each later row re-reads the stale slots that precede its true
+	 * start.  Only inputs with repeated (i,j) cancelling mod p are affected; being a drop-in means
+	 * producing the same CSR as the reference on those too. */
 	if (valued) {
 		i64 w = 0;
-		i64 begin = 0;
 		for (int i = 0; i < n; i++) {
 			i64 end = Cp[i + 1];
-			for (i64 k = begin; k < end; k++)
+			for (i64 k = w; k < end; k++)
 				if (Cx[k] != 0) {
 					Cj[w] = Cj[k];
 					Cx[w] = Cx[k];
 					w += 1;
 				}
-			begin = end;
 			Cp[i + 1] = w;
 		}
 	}
