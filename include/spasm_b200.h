@@ -1,0 +1,60 @@
+/*
+ * spasm_b200.h -- extra C-ABI entry points of libspasm_b200.so.
+ *
+ * These do not exist in the reference; they expose what the benchmark and the
+ * tests need to *measure* the CUDA path (device selection, per-phase CUDA-event
+ * timers, kernel launch counts, algorithmic byte counters of SURVEY.md 8d).
+ * The drop-in surface proper is include/spasm.h.
+ */
+#ifndef _SPASM_B200_H
+#define _SPASM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-process counters, reset with spasm_b200_reset_stats().  All times are CUDA-event
+ * milliseconds measured on the library's stream. */
+struct spasm_b200_stats {
+	int64_t kernel_launches;      /* kernels of this library launched since the last reset */
+	double ms_pivots;             /* FL + FL-columns + greedy + reorder + U extraction */
+	double ms_pivots_greedy;      /*   of which the greedy cycle-free search */
+	double ms_solve;              /* batched triangular solves (all callers) */
+	double ms_dense;              /* dense echelon + dense updates */
+	double ms_dense_gemm;         /*   of which the trailing-update / block-update GEMMs */
+	double ms_total_echelonize;   /* wall clock of the last spasm_echelonize call */
+	/* algorithmic work */
+	double solve_bytes;           /* sum over solved rows of 8*nnz(B[k]) + 8*sum nnz(U rows reached) + output bytes */
+	int64_t solve_rows;
+	int64_t solve_batches;
+	double solve_traffic_model;   /* bytes the batched formulation itself has to move (panel reads + writes) */
+	double gemm_fieldops;         /* 2*M*N*K of every dense update executed */
+	double gemm_int8_ops;         /* limb products actually issued to the int8 tensor pipe (0 when on CUDA cores) */
+	int64_t greedy_edges;         /* pivot-row entries traversed by the greedy search */
+	int64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe by the library */
+	/* trace of the last spasm_echelonize call, for parity with the oracle */
+	int nrounds;
+	int found_FL[64], found_FLcol[64], found_greedy[64];
+	double density[64];
+	int finish;                   /* 0 none, 1 low-rank, 2 dense, 3 GPLU (executed through the dense path) */
+	int nblocks;
+	int block_Sn[4096], block_Sm[4096], block_rr[4096], block_w[4096];
+	int dag_depth;                /* number of levels of the last structural U */
+};
+
+int  spasm_b200_device_count(void);
+void spasm_b200_set_device(int device);      /* default: SPASM_B200_DEVICE or LOCAL_RANK or 0 */
+void spasm_b200_reset_stats(void);
+void spasm_b200_get_stats(struct spasm_b200_stats *out);
+const char *spasm_b200_version(void);
+void spasm_b200_set_verbose(int verbose);    /* 0 silences the stderr progress lines */
+
+/* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
+ * round after round; returns their number.  Pass NULL to query the count. */
+int spasm_b200_last_pivot_pairs(int *rows, int *cols, int *round_start /* size nrounds+1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

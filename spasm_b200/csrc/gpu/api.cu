@@ -1,0 +1,411 @@
+/*
+ * The remaining GPU entry points of include/spasm.h, as thin host wrappers:
+ * they move the caller's host matrices to HBM, run the same kernel families as
+ * spasm_echelonize, and hand back malloc'ed host results.
+ */
+#include <math.h>
+#include "engine.cuh"
+#include "stats.cuh"
+
+namespace sb {
+int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round);
+double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R);
+void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S);
+
+#define LOG(...) do { if (ctx().verbose) { fprintf(stderr, __VA_ARGS__); fflush(stderr); } } while (0)
+
+/* engine over a caller-provided echelon form (host U + qinv) */
+static void engine_from_host(Engine &E, const struct spasm_csr *U, const int *qinv)
+{
+	E.init(U->m, spasm_get_prime(U));
+	if (U->n > 0) {
+		struct spasm_csr view = *U;
+		E.U.upload(&view);
+	}
+	E.U.m = U->m;
+	E.U.prime = spasm_get_prime(U);
+	E.Uqinv.upload(qinv, (size_t) U->m, ctx().stream);
+	E.rebuild_schedule();
+}
+
+/* device CSR -> malloc'ed host CSR with n rows */
+static struct spasm_csr *csr_to_host(const DevCsr &S)
+{
+	struct spasm_csr *H = spasm_csr_alloc(S.n, S.m, std::max<i64>(S.nnz, 1), S.prime, true);
+	cudaStream_t s = ctx().stream;
+	S.p.download(H->p, (size_t) S.n + 1, s);
+	S.j.download(H->j, (size_t) S.nnz, s);
+	S.x.download(H->x, (size_t) S.nnz, s);
+	sync();
+	stats().pub.d2h_bytes += S.nnz * 8 + (i64) (S.n + 1) * 8;
+	spasm_csr_realloc(H, -1);
+	return H;
+}
+
+/* concatenate per-batch CSR pieces (device) into one host CSR */
+struct HostPiece {
+	std::vector<i64> p;
+	std::vector<int> j;
+	std::vector<i32> x;
+};
+
+static void piece_download(const DevBuf<i64> &Sp, const DevBuf<int> &Sj, const DevBuf<i32> &Sx, int rows, i64 nnz, HostPiece &out)
+{
+	cudaStream_t s = ctx().stream;
+	out.p.resize((size_t) rows + 1);
+	out.j.resize((size_t) nnz);
+	out.x.resize((size_t) nnz);
+	Sp.download(out.p.data(), (size_t) rows + 1, s);
+	Sj.download(out.j.data(), (size_t) nnz, s);
+	Sx.download(out.x.data(), (size_t) nnz, s);
+	sync();
+	stats().pub.d2h_bytes += nnz * 8 + (i64) (rows + 1) * 8;
+}
+
+static struct spasm_csr *pieces_to_host(const std::vector<HostPiece> &pieces, int n, int m, i64 prime)
+{
+	i64 total = 0;
+	for (const HostPiece &pc : pieces)
+		total += (i64) pc.j.size();
+	struct spasm_csr *H = spasm_csr_alloc(n, m, std::max<i64>(total, 1), prime, true);
+	i64 off = 0;
+	int row = 0;
+	for (const HostPiece &pc : pieces) {
+		int rows = (int) pc.p.size() - 1;
+		for (int t = 0; t < rows; t++)
+			H->p[row + t + 1] = off + pc.p[t + 1];
+		memcpy(H->j + off, pc.j.data(), pc.j.size() * sizeof(int));
+		memcpy(H->x + off, pc.x.data(), pc.x.size() * sizeof(i32));
+		off += (i64) pc.j.size();
+		row += rows;
+	}
+	for (; row < n; row++)
+		H->p[row + 1] = off;
+	spasm_csr_realloc(H, -1);
+	return H;
+}
+
+static void store_dense(void *S, spasm_datatype datatype, const std::vector<i32> &host, int rows, int ld, int Sm)
+{
+	for (int r = 0; r < rows; r++)
+		for (int c = 0; c < Sm; c++)
+			spasm_datatype_write(S, (size_t) r * Sm + c, datatype, host[(size_t) r * ld + c]);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+/* reference: src/spasm_pivots.c:369-448 */
+int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, struct spasm_lu *fact, int *p, struct echelonize_opts *opts)
+{
+	struct echelonize_opts defaults;
+	if (opts == NULL) {
+		spasm_echelonize_init_opts(&defaults);
+		opts = &defaults;
+	}
+	if (fact->Ltmp != NULL)
+		errx(1, "[spasm-b200] spasm_pivots_extract_structural: the L path is not part of the B200 build");
+	ctx();
+	struct spasm_csr *U = fact->U;
+	Engine E;
+	E.init(A->m, spasm_get_prime(A));
+	if (U->n > 0)
+		E.U.upload(U);
+	E.Uqinv.upload(fact->qinv, (size_t) A->m, ctx().stream);
+	int un0 = U->n;
+	i64 unz0 = spasm_nnz(U);
+	DevCsr dA;
+	dA.upload(A);
+	stats().pair_row.clear();
+	stats().pair_col.clear();
+	int npiv = extract_structural(E, dA, p_in, p, opts->enable_greedy_pivot_search, 0);
+	/* append the new rows to the caller's U */
+	i64 extra = E.U.nnz - unz0;
+	if (spasm_nnz(U) + extra > U->nzmax)
+		spasm_csr_realloc(U, spasm_nnz(U) + extra);
+	cudaStream_t s = ctx().stream;
+	std::vector<i64> hp((size_t) npiv + 1);
+	if (npiv > 0) {
+		CUDA_CHECK(cudaMemcpyAsync(hp.data(), E.U.p.ptr + un0, ((size_t) npiv + 1) * sizeof(i64), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(U->j + unz0, E.U.j.ptr + unz0, (size_t) extra * sizeof(int), cudaMemcpyDeviceToHost, s));
+		CUDA_CHECK(cudaMemcpyAsync(U->x + unz0, E.U.x.ptr + unz0, (size_t) extra * sizeof(i32), cudaMemcpyDeviceToHost, s));
+		sync();
+		for (int k = 0; k < npiv; k++)
+			U->p[un0 + k + 1] = hp[k + 1];
+		U->n = un0 + npiv;
+	}
+	E.Uqinv.download(fact->qinv, (size_t) A->m, s);
+	sync();
+	return npiv;
+}
+
+/* reference: src/spasm_schur.c:11-44 */
+double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int n, const struct spasm_csr *U, const int *qinv, int R)
+{
+	if (n == 0)
+		return 0;
+	ctx();
+	Engine E;
+	engine_from_host(E, U, qinv);
+	DevCsr dA;
+	dA.upload(A);
+	return estimate_density(E, dA, p, n, R);
+}
+
+/* reference: src/spasm_schur.c:61-193 */
+struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, const struct spasm_lu *fact,
+                              double est_density, struct spasm_triplet *L, const int *p_in, int *p_out)
+{
+	if (L != NULL)
+		errx(1, "[spasm-b200] spasm_schur: the L path is not part of the B200 build");
+	ctx();
+	Engine E;
+	engine_from_host(E, fact->U, fact->qinv);
+	DevCsr dA;
+	dA.upload(A);
+	if (est_density < 0)
+		est_density = estimate_density(E, dA, p, n, 100);     /* keeps the reference's rand() consumption */
+	DevCsr S;
+	schur_sparse(E, dA, p, n, S);
+	if (p_out != NULL)
+		for (int k = 0; k < n; k++)
+			p_out[k] = (p_in != NULL) ? p_in[p[k]] : p[k];
+	LOG("Schur complement: %d * %d [%" PRId64 " nz / density= %.3f]\n", n, A->m, S.nnz, 1.0 * S.nnz / (1.0 * A->m * n));
+	return csr_to_host(S);
+}
+
+/* reference: src/spasm_schur.c:257-333 */
+void spasm_schur_dense(const struct spasm_csr *A, const int *p, int n, const int *p_in,
+                       struct spasm_lu *fact, void *S, spasm_datatype datatype, int *q, int *p_out)
+{
+	if (fact->Ltmp != NULL)
+		errx(1, "[spasm-b200] spasm_schur_dense: the L path is not part of the B200 build");
+	ctx();
+	Engine E;
+	engine_from_host(E, fact->U, fact->qinv);
+	E.begin_dense();
+	int Sm = E.Sm0;
+	for (int c = 0; c < Sm; c++)
+		q[c] = E.q0[c];
+	LOG("[schur/dense] dimension %d x %d...\n", n, Sm);
+	DevCsr dA;
+	dA.upload(A);
+	cudaStream_t s = ctx().stream;
+	const int cap = panel_capacity(E.m);
+	int ld = (Sm + 3) & ~3;
+	DevBuf<i32> B;
+	std::vector<i32> host;
+	for (int done = 0; done < n; done += cap) {
+		int R = std::min(cap, n - done);
+		DevBuf<int> d_rows;
+		d_rows.upload(p + done, (size_t) R, s);
+		E.solve_rows(dA, d_rows.ptr, R, false);
+		B.ensure((size_t) R * std::max(ld, 4));
+		E.gather_q0(B.ptr, ld);
+		host.resize((size_t) R * std::max(ld, 4));
+		B.download(host.data(), (size_t) R * ld, s);
+		sync();
+		stats().pub.d2h_bytes += (i64) R * ld * 4;
+		char *dst = (char *) S + (size_t) done * Sm * spasm_datatype_size(datatype);
+		store_dense(dst, datatype, host, R, ld, Sm);
+	}
+	for (int k = 0; k < n; k++)
+		p_out[k] = (p_in != NULL) ? p_in[p[k]] : p[k];
+}
+
+/* reference: src/spasm_schur.c:346-413 */
+void spasm_schur_dense_randomized(const struct spasm_csr *A, const int *p, int n, const struct spasm_csr *U, const int *qinv,
+                                  void *S, spasm_datatype datatype, int *q, int N, int w)
+{
+	ctx();
+	Engine E;
+	engine_from_host(E, U, qinv);
+	E.begin_dense();
+	int Sm = E.Sm0;
+	for (int c = 0; c < Sm; c++)
+		q[c] = E.q0[c];
+	LOG("[schur/dense/random] dimension %d x %d, weight %d...\n", N, Sm, w);
+	DevCsr dA;
+	dA.upload(A);
+	cudaStream_t s = ctx().stream;
+	int ww = (w <= 0) ? n : w;
+	std::vector<int> rows((size_t) N * ww);
+	std::vector<i32> coef((size_t) N * ww);
+	i64 prime = spasm_get_prime(A);
+	for (int k = 0; k < N; k++) {
+		spasm_prng_ctx prng;
+		spasm_prng_seed_simple(prime, (u64) k, 0, &prng);
+		for (int t = 0; t < ww; t++) {
+			if (w <= 0) {
+				rows[(size_t) k * ww + t] = p[t];
+				coef[(size_t) k * ww + t] = spasm_prng_ZZp(&prng);
+			} else {
+				rows[(size_t) k * ww + t] = p[rand() % n];
+				coef[(size_t) k * ww + t] = (t == 0) ? 1 : spasm_prng_ZZp(&prng);
+			}
+		}
+	}
+	DevBuf<int> d_rows;
+	DevBuf<i32> d_coef;
+	d_rows.upload(rows.data(), rows.size(), s);
+	d_coef.upload(coef.data(), coef.size(), s);
+	E.solve_combos(dA, d_rows.ptr, d_coef.ptr, N, ww);
+	int ld = (Sm + 3) & ~3;
+	DevBuf<i32> B((size_t) N * std::max(ld, 4));
+	E.gather_q0(B.ptr, ld);
+	std::vector<i32> host((size_t) N * std::max(ld, 4));
+	B.download(host.data(), (size_t) N * ld, s);
+	sync();
+	store_dense(S, datatype, host, N, ld, Sm);
+}
+
+/* reference: src/spasm_ffpack.cpp:78-86 (boundary) -- computed by dense.cu */
+int spasm_ffpack_rref(i64 prime, int n, int m, void *A, int ldA, spasm_datatype datatype, size_t *qinv)
+{
+	ctx();
+	cudaStream_t s = ctx().stream;
+	Zp F = make_zp(prime);
+	int ld = (m + 3) & ~3;
+	std::vector<i32> host((size_t) std::max(n, 1) * std::max(ld, 4), 0);
+	spasm_field field;
+	spasm_field_init(prime, field);
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < m; j++)
+			host[(size_t) i * ld + j] = spasm_ZZp_init(field, (i64) spasm_datatype_read(A, (size_t) i * ldA + j, datatype));
+	DevBuf<i32> D;
+	D.upload(host.data(), host.size(), s);
+	RrefResult res = dense_rref(D.ptr, n, m, ld, F);
+	D.download(host.data(), host.size(), s);
+	sync();
+	std::vector<char> is_pivot((size_t) std::max(m, 1), 0);
+	for (int t = 0; t < res.rank; t++) {
+		qinv[t] = res.pivcol[t];
+		is_pivot[res.pivcol[t]] = 1;
+	}
+	int k = res.rank;
+	for (int j = 0; j < m; j++)
+		if (!is_pivot[j])
+			qinv[k++] = j;
+	/* packed layout of the reference's consumers: row i, position k >= rank  <->  column qinv[k] */
+	std::vector<i32> packed((size_t) std::max(n, 1) * std::max(m, 1), 0);
+	for (int t = 0; t < res.rank; t++) {
+		const i32 *row = host.data() + (size_t) res.pivrow[t] * ld;
+		for (int kk = 0; kk < m; kk++)
+			packed[(size_t) t * m + kk] = (kk < res.rank) ? (kk == t) : row[qinv[kk]];
+	}
+	for (int i = 0; i < n; i++)
+		for (int kk = 0; kk < m; kk++)
+			spasm_datatype_write(A, (size_t) i * ldA + kk, datatype, packed[(size_t) i * m + kk]);
+	return res.rank;
+}
+
+/* reference: src/spasm_rref.c:22-146 */
+struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
+{
+	const struct spasm_csr *U = fact->U;
+	int n = U->n, m = U->m;
+	char hnnz[8];
+	spasm_human_format(spasm_nnz(U), hnnz);
+	LOG("[rref] start. U is %d x %d (%s nnz)\n", n, m, hnnz);
+	ctx();
+	Engine E;
+	engine_from_host(E, U, fact->qinv);
+	cudaStream_t s = ctx().stream;
+	std::vector<int> pivcol((size_t) std::max(n, 1));
+	for (int i = 0; i < n; i++)
+		pivcol[i] = U->j[U->p[i]];
+	const int cap = panel_capacity(m);
+	std::vector<HostPiece> pieces;
+	for (int done = 0; done < n; done += cap) {
+		int R = std::min(cap, n - done);
+		std::vector<int> rows(R);
+		for (int r = 0; r < R; r++)
+			rows[r] = done + r;
+		DevBuf<int> d_rows, d_first;
+		d_rows.upload(rows.data(), (size_t) R, s);
+		d_first.upload(pivcol.data() + done, (size_t) R, s);
+		/* row i is solved against U with its own pivot unregistered (rref.c:56-60): its pivot entry is not
+		 * scattered, so nothing propagates from it, and it is emitted first, as 1 */
+		E.solve_rows(E.U, d_rows.ptr, R, true);
+		DevBuf<i64> Sp;
+		DevBuf<int> Sj;
+		DevBuf<i32> Sx;
+		i64 nnz;
+		panel_to_csr(E.panel, E.Uqinv.ptr, d_first.ptr, 1, nullptr, Sp, Sj, Sx, nnz);
+		pieces.emplace_back();
+		piece_download(Sp, Sj, Sx, R, nnz, pieces.back());
+	}
+	struct spasm_csr *Rm = pieces_to_host(pieces, n, m, spasm_get_prime(U));
+	for (int j = 0; j < m; j++)
+		Rqinv[j] = -1;
+	for (int i = 0; i < n; i++)
+		Rqinv[Rm->j[Rm->p[i]]] = i;
+	spasm_human_format(spasm_nnz(Rm), hnnz);
+	LOG("[rref] done. NNZ(R) = %s\n", hnnz);
+	return Rm;
+}
+
+/* reference: src/spasm_kernel.c:9-127 */
+struct spasm_csr *spasm_kernel(const struct spasm_lu *fact)
+{
+	const struct spasm_csr *U = fact->U;
+	const int *qinv = fact->qinv;
+	int n = U->n, m = U->m;
+	char hnnz[8];
+	spasm_human_format(spasm_nnz(U), hnnz);
+	LOG("[kernel] start. U is %d x %d (%s nnz)\n", n, m, hnnz);
+	ctx();
+	cudaStream_t s = ctx().stream;
+	Engine E;
+	E.init(m, spasm_get_prime(U));
+	if (n > 0)
+		E.U.upload(U);
+	E.Uqinv.upload(qinv, (size_t) m, s);
+	DepGraph Gt;
+	depgraph_transposed(E.U, E.Uqinv.ptr, Gt);
+	depgraph_schedule(Gt);
+	std::vector<int> pivcol((size_t) std::max(n, 1));
+	for (int i = 0; i < n; i++)
+		pivcol[i] = U->j[U->p[i]];
+	DevBuf<int> d_pivcol;
+	d_pivcol.upload(pivcol.data(), pivcol.size(), s);
+	std::vector<int> freecols;
+	for (int j = 0; j < m; j++)
+		if (qinv[j] < 0)
+			freecols.push_back(j);
+	const int cap = panel_capacity(std::max(n, 1));
+	std::vector<HostPiece> pieces;
+	std::vector<int> colslot((size_t) std::max(m, 1));
+	Panel P;
+	for (size_t done = 0; done < freecols.size(); done += cap) {
+		int R = (int) std::min<size_t>(cap, freecols.size() - done);
+		std::fill(colslot.begin(), colslot.end(), -1);
+		for (int r = 0; r < R; r++)
+			colslot[freecols[done + r]] = r;
+		DevBuf<int> d_slot, d_first;
+		d_slot.upload(colslot.data(), colslot.size(), s);
+		d_first.upload(freecols.data() + done, (size_t) R, s);
+		GpuTimer t;
+		t.start();
+		P.shape(n, R);
+		panel_scatter_columns(E.U, d_slot.ptr, P);
+		panel_solve(Gt, P.X, P.ld, R, E.F);
+		stats().pub.ms_solve += t.stop_ms();
+		DevBuf<i64> Sp;
+		DevBuf<int> Sj;
+		DevBuf<i32> Sx;
+		i64 nnz;
+		panel_to_csr(P, nullptr, d_first.ptr, -1, d_pivcol.ptr, Sp, Sj, Sx, nnz);
+		pieces.emplace_back();
+		piece_download(Sp, Sj, Sx, R, nnz, pieces.back());
+	}
+	struct spasm_csr *K = pieces_to_host(pieces, m - n, m, spasm_get_prime(U));
+	spasm_human_format(spasm_nnz(K), hnnz);
+	LOG("[kernel] done. NNZ(K) = %s\n", hnnz);
+	return K;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,127 @@
+/*
+ * Shared plumbing of the CUDA side: error convention, device buffers, device CSR, timers.
+ * Everything here is internal to libspasm_b200.so; the public boundary is include/spasm.h.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <err.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+extern "C" {
+#include "spasm.h"
+}
+
+/* The reference reports fatal conditions with err()/errx() and exit status 1
+ * (reference: src/spasm_util.c:65-87); CUDA failures follow the same convention. */
+#define CUDA_CHECK(call)                                                                              \
+	do {                                                                                              \
+		cudaError_t e_ = (call);                                                                      \
+		if (e_ != cudaSuccess)                                                                        \
+			errx(1, "[spasm-b200] CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+			     cudaGetErrorString(e_));                                                             \
+	} while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+namespace sb {
+
+/* -------------------------------------------------------------------- device context */
+struct Context {
+	int device = -1;
+	int sm_count = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	bool verbose = true;
+};
+Context &ctx();            /* lazily initialised; aborts when no usable sm_100 device */
+
+/* -------------------------------------------------------------------- statistics (include/spasm_b200.h) */
+struct Stats;
+Stats &stats();
+
+/* -------------------------------------------------------------------- device buffers */
+template <typename T> struct DevBuf {
+	T *ptr = nullptr;
+	size_t count = 0;
+	DevBuf() {}
+	explicit DevBuf(size_t n) { alloc(n); }
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	DevBuf(DevBuf &&o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr; o.count = 0; }
+	DevBuf &operator=(DevBuf &&o) noexcept {
+		if (this != &o) {
+			release();
+			ptr = o.ptr; count = o.count;
+			o.ptr = nullptr; o.count = 0;
+		}
+		return *this;
+	}
+	~DevBuf() { release(); }
+	void alloc(size_t n) {
+		release();
+		count = n;
+		if (n > 0)
+			CUDA_CHECK(cudaMalloc((void **) &ptr, n * sizeof(T)));
+	}
+	/* grow (contents are NOT preserved) */
+	void ensure(size_t n) { if (n > count) alloc(n); }
+	void release() {
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		count = 0;
+	}
+	void zero(cudaStream_t s) { if (count) CUDA_CHECK(cudaMemsetAsync(ptr, 0, count * sizeof(T), s)); }
+	void fill_byte(int b, cudaStream_t s) { if (count) CUDA_CHECK(cudaMemsetAsync(ptr, b, count * sizeof(T), s)); }
+	void upload(const T *host, size_t n, cudaStream_t s) {
+		ensure(n);
+		if (n) CUDA_CHECK(cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+	}
+	void download(T *host, size_t n, cudaStream_t s) const {
+		if (n) CUDA_CHECK(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+	}
+	operator T *() const { return ptr; }
+};
+
+inline void sync() { CUDA_CHECK(cudaStreamSynchronize(ctx().stream)); }
+
+template <typename T> inline T fetch(const T *dptr) {
+	T v;
+	CUDA_CHECK(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+	sync();
+	return v;
+}
+
+/* -------------------------------------------------------------------- device CSR */
+struct DevCsr {
+	int n = 0, m = 0;
+	i64 nnz = 0;
+	DevBuf<i64> p;
+	DevBuf<int> j;
+	DevBuf<i32> x;
+	i64 prime = 0;
+	void upload(const struct spasm_csr *A);
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned) ((a + b - 1) / b); }
+
+/* CUDA-event timer on the library's stream */
+struct GpuTimer {
+	cudaEvent_t a, b;
+	GpuTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+	~GpuTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+	void start() { cudaEventRecord(a, ctx().stream); }
+	double stop_ms() {
+		cudaEventRecord(b, ctx().stream);
+		cudaEventSynchronize(b);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, a, b);
+		return ms;
+	}
+};
+
+}  // namespace sb

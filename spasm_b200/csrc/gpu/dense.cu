@@ -1,0 +1,423 @@
+#include <cub/cub.cuh>
+#include "dense.cuh"
+#include "stats.cuh"
+
+namespace sb {
+
+/* ================================================================== C -= A * B (mod p), CUDA cores
+ * 64 x 64 tile per CTA, 256 threads, 4 x 4 outputs per thread, K in slabs of 32 staged in shared
+ * memory; 64-bit accumulators with delayed reduction (zp.cuh).  This is the portable path; the
+ * int8 tensor-core path (umma_gemm.cu) takes over for large products. */
+#define GM 64
+#define GN 64
+#define GK 32
+
+__global__ void __launch_bounds__(256)
+k_gemm_sub(i32 *__restrict__ C, int ldc, const i32 *__restrict__ A, int lda, const i32 *__restrict__ B, int ldb,
+           int M, int N, int K, Zp F, const int *d_K)
+{
+	if (d_K)
+		K = min(K, *d_K);
+	if (K <= 0)
+		return;
+	__shared__ i32 As[GK][GM + 4];
+	__shared__ i32 Bs[GK][GN + 4];
+	const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+	const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+	i64 acc[4][4];
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++)
+			acc[a][b] = 0;
+	int pending = 0;
+	for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+		for (int t = 0; t < (GM * GK) / 256; t++) {
+			int idx = tid + t * 256;
+			int mm = idx / GK, kk = idx % GK;
+			int gm = m0 + mm, gk = k0 + kk;
+			As[kk][mm] = (gm < M && gk < K) ? A[(size_t) gm * lda + gk] : 0;
+		}
+#pragma unroll
+		for (int t = 0; t < (GK * GN) / 256; t++) {
+			int idx = tid + t * 256;
+			int kk = idx / GN, nn = idx % GN;
+			int gk = k0 + kk, gn = n0 + nn;
+			Bs[kk][nn] = (gk < K && gn < N) ? B[(size_t) gk * ldb + gn] : 0;
+		}
+		__syncthreads();
+#pragma unroll 4
+		for (int kk = 0; kk < GK; kk++) {
+			i32 a[4], b[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				a[u] = As[kk][ty * 4 + u];
+				b[u] = Bs[kk][tx * 4 + u];
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int v = 0; v < 4; v++)
+					acc[u][v] += (i64) a[u] * (i64) b[v];
+			if (++pending >= F.delay) {
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+#pragma unroll
+					for (int v = 0; v < 4; v++)
+						acc[u][v] = zp_reduce(acc[u][v], F);
+				pending = 0;
+			}
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int u = 0; u < 4; u++) {
+		int gm = m0 + ty * 4 + u;
+		if (gm >= M)
+			continue;
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			int gn = n0 + tx * 4 + v;
+			if (gn < N) {
+				size_t at = (size_t) gm * ldc + gn;
+				C[at] = zp_reduce((i64) C[at] - (i64) zp_reduce(acc[u][v], F), F);
+			}
+		}
+	}
+}
+
+void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F, const int *d_K)
+{
+	if (M <= 0 || N <= 0 || K <= 0)
+		return;
+	dim3 grid(cdiv(N, GN), cdiv(M, GM));
+	k_gemm_sub<<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+	if (!d_K)
+		stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
+}
+
+/* ================================================================== gathers */
+
+__global__ void k_gather_columns(const i32 *__restrict__ src, int lds, int rows, const int *__restrict__ cols, int ncols, i32 *dst, int ldd)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+	if (t < ncols && r < rows)
+		dst[(size_t) r * ldd + t] = src[(size_t) r * lds + cols[t]];
+}
+
+void dense_gather_columns(const i32 *src, int lds, int rows, const int *d_cols, int ncols, i32 *dst, int ldd)
+{
+	if (rows <= 0 || ncols <= 0)
+		return;
+	dim3 grid(cdiv(ncols, 256), rows);
+	k_gather_columns<<<grid, 256, 0, ctx().stream>>>(src, lds, rows, d_cols, ncols, dst, ldd);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+}
+
+__global__ void k_gather_rows(const i32 *__restrict__ src, int lds, const int *__restrict__ rows, int nrows, int width, i32 *dst, int ldd,
+                              const int *d_nrows)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+	if (d_nrows)
+		nrows = min(nrows, *d_nrows);
+	if (c < width && t < nrows)
+		dst[(size_t) t * ldd + c] = src[(size_t) rows[t] * lds + c];
+}
+
+void dense_gather_rows(const i32 *src, int lds, const int *d_rows, int nrows, int width, i32 *dst, int ldd)
+{
+	if (nrows <= 0 || width <= 0)
+		return;
+	dim3 grid(cdiv(width, 256), nrows);
+	k_gather_rows<<<grid, 256, 0, ctx().stream>>>(src, lds, d_rows, nrows, width, dst, ldd, nullptr);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+}
+
+/* ================================================================== panel factorisation */
+
+#define NB 32
+#define PSTRIDE 33
+
+struct PanelInfo {
+	int k;
+	int prow[NB];
+	int pcol[NB];
+};
+
+/*
+ * One CTA.  Works on a private copy of the panel S[:, c0:c0+nb]:
+ *   1. discovers the pivots of the panel by forward elimination on the rows that are not pivotal yet
+ *      (first such row with a non-zero entry, column by column)            -> prow[], pcol[], k
+ *   2. inverts M = S[prow, c0 + pcol] (k x k)
+ *   3. writes the multipliers W (n x NB): the update of the whole matrix is  S <- S - W * S[prow, :]
+ *      (rows outside the panel's pivots: W = S[:, pivot columns] * M^-1; pivot rows: W = I - M^-1)
+ * and records the new pivots (rowstate, pivcol list, rank counter).
+ */
+__global__ void __launch_bounds__(1024)
+k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowstate, int *rank_dev, int *pivcol_out,
+             i32 *W, PanelInfo *info, i32 *scratch, int use_smem, Zp F)
+{
+	extern __shared__ unsigned char dyn[];
+	__shared__ int s_min, s_k, s_inv;
+	__shared__ int s_prow[NB], s_pcol[NB];
+	__shared__ i64 Mw[NB][2 * NB + 1];
+	const int tid = threadIdx.x, T = blockDim.x;
+	const int r0 = *rank_dev;
+	if (r0 >= n || c0 >= m) {
+		if (tid == 0)
+			info->k = 0;
+		return;
+	}
+	const int nbw = min(NB, m - c0);
+	i32 *Pw = use_smem ? (i32 *) dyn : scratch;
+	unsigned char *taken = use_smem ? (dyn + (size_t) n * PSTRIDE * sizeof(i32)) : (unsigned char *) (scratch + (size_t) n * PSTRIDE);
+
+	for (int idx = tid; idx < n * NB; idx += T) {
+		int i = idx / NB, c = idx % NB;
+		Pw[i * PSTRIDE + c] = (c < nbw) ? S[(size_t) i * ld + c0 + c] : 0;
+	}
+	for (int i = tid; i < n; i += T)
+		taken[i] = rowstate[i] >= 0;
+	if (tid == 0)
+		s_k = 0;
+	__syncthreads();
+
+	for (int c = 0; c < nbw; c++) {
+		if (s_k + r0 >= n)
+			break;
+		if (tid == 0)
+			s_min = 0x7fffffff;
+		__syncthreads();
+		for (int i = tid; i < n; i += T)
+			if (!taken[i] && Pw[i * PSTRIDE + c] != 0) {
+				atomicMin(&s_min, i);
+				break;
+			}
+		__syncthreads();
+		const int piv = s_min;
+		if (piv == 0x7fffffff) {
+			__syncthreads();
+			continue;
+		}
+		if (tid == 0) {
+			s_prow[s_k] = piv;
+			s_pcol[s_k] = c;
+			s_k += 1;
+			taken[piv] = 1;
+			s_inv = zp_inverse(Pw[piv * PSTRIDE + c], F);
+		}
+		__syncthreads();
+		const i32 inv = s_inv;
+		for (int i = tid; i < n; i += T) {
+			if (taken[i])
+				continue;
+			i32 l = Pw[i * PSTRIDE + c];
+			if (l == 0)
+				continue;
+			l = zp_mul(l, inv, F);
+			for (int cc = c; cc < nbw; cc++)
+				Pw[i * PSTRIDE + cc] = zp_reduce((i64) Pw[i * PSTRIDE + cc] - (i64) l * Pw[piv * PSTRIDE + cc], F);
+		}
+		__syncthreads();
+	}
+	__syncthreads();
+	const int k = s_k;
+	if (tid == 0)
+		info->k = k;
+	if (k == 0)
+		return;
+
+	/* --- M^-1 by Gauss-Jordan on [M | I] */
+	for (int idx = tid; idx < k * 2 * NB; idx += T) {
+		int s = idx / (2 * NB), t = idx % (2 * NB);
+		i64 v = 0;
+		if (t < k)
+			v = S[(size_t) s_prow[s] * ld + c0 + s_pcol[t]];
+		else if (t >= NB)
+			v = (t - NB == s);
+		Mw[s][t] = v;
+	}
+	__syncthreads();
+	for (int t = 0; t < k; t++) {
+		if (tid == 0) {
+			int s = t;
+			while (Mw[s][t] == 0)
+				s++;                         /* M is invertible: a non-zero entry exists below */
+			if (s != t)
+				for (int c = 0; c < 2 * NB; c++) {
+					i64 tmp = Mw[s][c];
+					Mw[s][c] = Mw[t][c];
+					Mw[t][c] = tmp;
+				}
+			s_inv = zp_inverse((i32) Mw[t][t], F);
+		}
+		__syncthreads();
+		if (tid < 2 * NB)
+			Mw[t][tid] = zp_mul((i32) Mw[t][tid], s_inv, F);
+		__syncthreads();
+		for (int idx = tid; idx < k * 2 * NB; idx += T) {
+			int s = idx / (2 * NB), c = idx % (2 * NB);
+			if (s == t)
+				continue;
+			i64 l = Mw[s][t];
+			/* all threads of row s read Mw[s][t] before any of them rewrites it: column t is rewritten by c == t only */
+			if (l != 0 && c != t)
+				Mw[s][c] = zp_reduce(Mw[s][c] - l * Mw[t][c], F);
+		}
+		__syncthreads();
+		for (int s = tid; s < k; s += T)
+			if (s != t)
+				Mw[s][t] = 0;
+		__syncthreads();
+	}
+
+	/* --- multipliers */
+	for (int idx = tid; idx < n * NB; idx += T) {
+		int i = idx / NB, t = idx % NB;
+		i32 w = 0;
+		if (t < k) {
+			int mine = -1;
+			for (int s = 0; s < k; s++)
+				if (s_prow[s] == i)
+					mine = s;
+			if (mine >= 0) {
+				w = zp_reduce((i64) (mine == t) - Mw[mine][NB + t], F);
+			} else {
+				i64 acc = 0;
+				for (int s = 0; s < k; s++)
+					acc = zp_reduce(acc + (i64) zp_mul(S[(size_t) i * ld + c0 + s_pcol[s]], (i32) Mw[s][NB + t], F), F);
+				w = (i32) acc;
+			}
+		}
+		W[(size_t) i * NB + t] = w;
+	}
+	if (tid < k) {
+		info->prow[tid] = s_prow[tid];
+		info->pcol[tid] = s_pcol[tid];
+		rowstate[s_prow[tid]] = r0 + tid;
+		pivcol_out[r0 + tid] = c0 + s_pcol[tid];
+	}
+	__syncthreads();
+	if (tid == 0)
+		*rank_dev = r0 + k;
+}
+
+/* P[t][j] = S[prow[t]][c0 + j] */
+__global__ void k_copy_pivot_rows(const i32 *__restrict__ S, int ld, int c0, int width, const PanelInfo *__restrict__ info, i32 *P, int ldp)
+{
+	int t = blockIdx.y;
+	if (t >= info->k)
+		return;
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < width)
+		P[(size_t) t * ldp + j] = S[(size_t) info->prow[t] * ld + c0 + j];
+}
+
+RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
+{
+	RrefResult out;
+	if (n <= 0 || m <= 0)
+		return out;
+	cudaStream_t s = ctx().stream;
+	DevBuf<int> rowstate((size_t) n), rank_dev(1), pivcol((size_t) m);
+	DevBuf<i32> W((size_t) n * NB), P((size_t) NB * (size_t) m);
+	DevBuf<PanelInfo> info(1);
+	rowstate.fill_byte(0xff, s);
+	rank_dev.zero(s);
+	size_t need = (size_t) n * PSTRIDE * sizeof(i32) + (size_t) n + 16;
+	int use_smem = need <= 200 * 1024;
+	DevBuf<i32> scratch(use_smem ? 1 : ((size_t) n * PSTRIDE + (size_t) n / 4 + 8));
+	if (use_smem)      /* static + dynamic shared memory may exceed the 48 KB default: always opt in */
+		CUDA_CHECK(cudaFuncSetAttribute(k_rref_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) need));
+	int panels = 0;
+	for (int c0 = 0; c0 < m; c0 += NB) {
+		int width = m - c0;
+		k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, W.ptr, info.ptr, scratch.ptr, use_smem, F);
+		dim3 g(cdiv(width, 256), NB);
+		k_copy_pivot_rows<<<g, 256, 0, s>>>(S, ld, c0, width, info.ptr, P.ptr, m);
+		LAUNCHED(2);
+		dense_gemm_sub(S + c0, ld, W.ptr, NB, P.ptr, m, n, width, NB, F, &info.ptr->k);
+		if (++panels % 8 == 0 && fetch(rank_dev.ptr) >= n)
+			break;
+	}
+	KERNEL_CHECK();
+	out.rank = fetch(rank_dev.ptr);
+	out.pivcol.resize(out.rank);
+	out.pivrow.assign(out.rank, -1);
+	std::vector<int> hs((size_t) n);
+	rowstate.download(hs.data(), (size_t) n, s);
+	pivcol.download(out.pivcol.data(), (size_t) out.rank, s);
+	sync();
+	for (int i = 0; i < n; i++)
+		if (hs[i] >= 0)
+			out.pivrow[hs[i]] = i;
+	stats().pub.gemm_fieldops += 2.0 * n * (double) m * out.rank;
+	return out;
+}
+
+/* ================================================================== dense rows -> sparse rows of U */
+
+template <bool EMIT>
+__global__ void k_rows_to_csr(const i32 *__restrict__ D, int ld, int nrows, int width, const int *__restrict__ pivcol,
+                              const unsigned char *__restrict__ skip, const int *__restrict__ colmap, i64 *len, const i64 *__restrict__ Rp, int *Rj, i32 *Rx)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (int t = warp; t < nrows; t += nwarps) {
+		const i32 *row = D + (size_t) t * ld;
+		i64 out = EMIT ? Rp[t] : 0;
+		if (EMIT && lane == 0) {
+			Rj[out] = colmap[pivcol[t]];
+			Rx[out] = 1;
+		}
+		i64 written = 1;
+		for (int c0 = 0; c0 < width; c0 += 32) {
+			int c = c0 + lane;
+			i32 v = (c < width && !skip[c]) ? row[c] : 0;
+			unsigned mask = __ballot_sync(0xffffffffu, v != 0);
+			if (EMIT && v != 0) {
+				i64 pos = out + written + __popc(mask & ((1u << lane) - 1));
+				Rj[pos] = colmap[c];
+				Rx[pos] = v;
+			}
+			written += __popc(mask);
+		}
+		if (!EMIT && lane == 0)
+			len[t] = written;
+	}
+}
+
+void dense_rows_to_csr(const i32 *D, int ld, int nrows, int width, const int *d_pivcol, const unsigned char *d_skip,
+                       const int *d_colmap, DevBuf<i64> &Rp, DevBuf<int> &Rj, DevBuf<i32> &Rx, i64 &nnz)
+{
+	cudaStream_t s = ctx().stream;
+	Rp.alloc((size_t) nrows + 1);
+	nnz = 0;
+	if (nrows == 0) {
+		CUDA_CHECK(cudaMemsetAsync(Rp.ptr, 0, sizeof(i64), s));
+		return;
+	}
+	DevBuf<i64> len((size_t) nrows + 1);
+	len.zero(s);
+	unsigned blocks = std::min(cdiv((size_t) nrows * 32, 256), 148u * 8);
+	k_rows_to_csr<false><<<blocks, 256, 0, s>>>(D, ld, nrows, width, d_pivcol, d_skip, d_colmap, len.ptr, nullptr, nullptr, nullptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, len.ptr, Rp.ptr, nrows + 1, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, len.ptr, Rp.ptr, nrows + 1, s);
+	LAUNCHED(2);
+	nnz = fetch(Rp.ptr + nrows);
+	Rj.alloc((size_t) nnz);
+	Rx.alloc((size_t) nnz);
+	k_rows_to_csr<true><<<blocks, 256, 0, s>>>(D, ld, nrows, width, d_pivcol, d_skip, d_colmap, nullptr, Rp.ptr, Rj.ptr, Rx.ptr);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+}
+
+}  // namespace sb

@@ -1,0 +1,106 @@
+/*
+ * Device context, statistics and the small extra C ABI of include/spasm_b200.h.
+ */
+#include "common.cuh"
+#include "stats.cuh"
+
+namespace sb {
+
+static Context g_ctx;
+static Stats g_stats;
+static int g_requested_device = -1;
+static bool g_verbose = true;
+
+Stats &stats() { return g_stats; }
+
+Context &ctx()
+{
+	if (g_ctx.device >= 0)
+		return g_ctx;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		errx(1, "[spasm-b200] no usable CUDA device (%s). This library has no CPU fallback: "
+		        "spasm_echelonize / spasm_rref / spasm_kernel / spasm_schur* run on a B200 (sm_100a) only.",
+		     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+	int dev = g_requested_device;
+	if (dev < 0) {
+		const char *s = getenv("SPASM_B200_DEVICE");
+		if (!s)
+			s = getenv("LOCAL_RANK");
+		dev = s ? atoi(s) % count : 0;
+	}
+	CUDA_CHECK(cudaSetDevice(dev));
+	cudaDeviceProp prop;
+	CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major != 10)
+		errx(1, "[spasm-b200] device %d (%s) is compute capability %d.%d; this build contains sm_100a code only",
+		     dev, prop.name, prop.major, prop.minor);
+	g_ctx.device = dev;
+	g_ctx.sm_count = prop.multiProcessorCount;
+	g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+	g_ctx.verbose = g_verbose;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+	return g_ctx;
+}
+
+void DevCsr::upload(const struct spasm_csr *A)
+{
+	cudaStream_t s = ctx().stream;
+	n = A->n;
+	m = A->m;
+	nnz = A->p[A->n];
+	prime = A->field->p;
+	p.upload(A->p, (size_t) n + 1, s);
+	j.upload(A->j, (size_t) nnz, s);
+	if (A->x)
+		x.upload(A->x, (size_t) nnz, s);
+	stats().pub.h2d_bytes += (i64) (n + 1) * 8 + nnz * 8;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int spasm_b200_device_count(void)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess)
+		return 0;
+	return count;
+}
+
+void spasm_b200_set_device(int device) { g_requested_device = device; }
+
+void spasm_b200_set_verbose(int verbose)
+{
+	g_verbose = verbose != 0;
+	if (g_ctx.device >= 0)
+		g_ctx.verbose = g_verbose;
+}
+
+void spasm_b200_reset_stats(void)
+{
+	std::vector<int> rows, cols;
+	g_stats = Stats();
+}
+
+void spasm_b200_get_stats(struct spasm_b200_stats *out) { *out = g_stats.pub; }
+
+const char *spasm_b200_version(void) { return "spasm-b200 r1 (sm_100a)"; }
+
+int spasm_b200_last_pivot_pairs(int *rows, int *cols, int *round_start)
+{
+	int n = (int) g_stats.pair_row.size();
+	if (rows)
+		memcpy(rows, g_stats.pair_row.data(), n * sizeof(int));
+	if (cols)
+		memcpy(cols, g_stats.pair_col.data(), n * sizeof(int));
+	if (round_start)
+		for (size_t k = 0; k < g_stats.pair_start.size(); k++)
+			round_start[k] = g_stats.pair_start[k];
+	return n;
+}
+}

@@ -1,0 +1,560 @@
+/*
+ * spasm_echelonize on the GPU: host orchestration (same decision logic as the
+ * reference, because the branch decisions are part of the result) driving the
+ * CUDA kernel families of pivots.cu / solve.cu / panel.cu / dense.cu.
+ * reference: src/spasm_echelonize.c
+ *
+ * What is restructured:
+ *  - all data stays in HBM between the steps: A, the structural rows of U, the
+ *    solve schedule, the dense rows; the host only sees counters;
+ *  - a dense block is reduced by the structural pivots with ONE batched sparse
+ *    solve and by the rows of the earlier dense blocks with dense products
+ *    (the reference scatters those dense rows one entry at a time,
+ *    spasm_schur.c:291-304 / :389-394 -- its dominant cost on config 1);
+ *  - U is assembled on the host once, at the end.
+ * What is kept bit for bit: option handling, round structure, thresholds,
+ * glibc rand() call sequence, PRNG coefficients, block sizes, weight doubling,
+ * the "n -= rr" quirk of the low-rank loop (echelonize.c:369).
+ */
+#include <math.h>
+#include <cub/cub.cuh>
+#include "engine.cuh"
+#include "stats.cuh"
+
+namespace sb {
+
+#define LOG(...) do { if (ctx().verbose) { fprintf(stderr, __VA_ARGS__); fflush(stderr); } } while (0)
+
+/* ------------------------------------------------------------------ small device helpers */
+
+struct IsPivotal {
+	__device__ bool operator()(const int &v) const { return v >= 0; }
+};
+
+/* rows_out = qinv[j] for the columns j (in the order of `cols`, or 0..m-1 when cols == NULL) with qinv[j] >= base */
+__global__ void k_select_rows(int count, const int *__restrict__ cols, const int *__restrict__ qinv, int *flags, int *rows)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+		return;
+	int j = cols ? cols[t] : t;
+	int i = qinv[j];
+	flags[t] = i >= 0;
+	rows[t] = i;
+}
+
+static int compact_flagged(const int *d_in, const int *d_flags, int count, int *d_out)
+{
+	static DevBuf<char> tmp;
+	DevBuf<int> nsel(1);
+	size_t bytes = 0;
+	cudaStream_t s = ctx().stream;
+	cub::DeviceSelect::Flagged(nullptr, bytes, d_in, d_flags, d_out, nsel.ptr, count, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceSelect::Flagged(tmp.ptr, bytes, d_in, d_flags, d_out, nsel.ptr, count, s);
+	LAUNCHED(1);
+	return fetch(nsel.ptr);
+}
+
+__global__ void k_add_offset(i64 *p, int count, i64 off)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < count)
+		p[t] += off;
+}
+
+/* ------------------------------------------------------------------ one round of structural pivots */
+
+/*
+ * reference: spasm_pivots_extract_structural (src/spasm_pivots.c:369-448).
+ * p (host, size A.n) receives the row permutation: pivotal rows first (in the order they get in U),
+ * then the other rows by increasing index.
+ */
+int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round)
+{
+	GpuTimer timer;
+	timer.start();
+	cudaStream_t s = ctx().stream;
+	const int n = A.n, m = A.m;
+	DevBuf<int> d_pinv((size_t) std::max(n, 1)), d_qinv((size_t) std::max(m, 1));
+	PivotCounts cnt = pivots_find(A, d_pinv.ptr, d_qinv.ptr, greedy);
+	int npiv = cnt.fl + cnt.flcol + cnt.greedy;
+	LOG("[pivots] Faugère-Lachartre: %d pivots found\n[pivots] ``Faugère-Lachartre on columns'': %d pivots found\n"
+	    "[pivots] greedy alternating cycle-free search: %d pivots found\n[pivots] %d pivots found\n",
+	    cnt.fl, cnt.flcol, cnt.greedy, npiv);
+	Stats &st = stats();
+	if (round < 64) {
+		st.pub.found_FL[round] = cnt.fl;
+		st.pub.found_FLcol[round] = cnt.flcol;
+		st.pub.found_greedy[round] = cnt.greedy;
+	}
+	std::vector<int> h_pinv((size_t) std::max(n, 1));
+	d_pinv.download(h_pinv.data(), (size_t) n, s);
+
+	std::vector<int> h_rows;       /* pivotal rows in their final order */
+	if (npiv > 0) {
+		/* 1. the new pivotal rows alone, in column order, give the dependency DAG among new pivots */
+		DevBuf<int> flags((size_t) m), rows_all((size_t) m), rows_tmp((size_t) npiv);
+		k_select_rows<<<cdiv(m, 256), 256, 0, s>>>(m, nullptr, d_qinv.ptr, flags.ptr, rows_all.ptr);
+		LAUNCHED(1);
+		int got = compact_flagged(rows_all.ptr, flags.ptr, m, rows_tmp.ptr);
+		if (got != npiv)
+			errx(1, "[spasm-b200] internal: pivot count mismatch (%d vs %d)", got, npiv);
+		DevCsr Unew;
+		Unew.m = m;
+		Unew.prime = A.prime;
+		DevBuf<int> scratch_qinv((size_t) m);
+		append_pivotal_rows(A, rows_tmp.ptr, npiv, d_pinv.ptr, Unew, scratch_qinv);
+		DepGraph Gnew;
+		depgraph_forward(Unew, Gnew);
+		depgraph_schedule(Gnew);
+		/* 2. pivot columns by (level, column) -> final order of the new rows */
+		DevBuf<int> flags2((size_t) m), rows_ord((size_t) m), rows_sorted((size_t) npiv);
+		k_select_rows<<<cdiv(m, 256), 256, 0, s>>>(m, Gnew.order.ptr, d_qinv.ptr, flags2.ptr, rows_ord.ptr);
+		LAUNCHED(1);
+		got = compact_flagged(rows_ord.ptr, flags2.ptr, m, rows_sorted.ptr);
+		if (got != npiv)
+			errx(1, "[spasm-b200] internal: pivot order mismatch");
+		bool first_rows = (E.U.n == 0);
+		append_pivotal_rows(A, rows_sorted.ptr, npiv, d_pinv.ptr, E.U, E.Uqinv);
+		h_rows.resize(npiv);
+		rows_sorted.download(h_rows.data(), (size_t) npiv, s);
+		sync();
+		if (first_rows) {
+			E.G = std::move(Gnew);           /* same columns, same dependencies: the schedule carries over */
+			E.G_ready = true;
+			st.pub.dag_depth = E.G.nlevels;
+		} else {
+			E.G_ready = false;
+		}
+	}
+	sync();
+	int k = 0;
+	for (int t = 0; t < npiv; t++) {
+		int i = h_rows[t];
+		p[k++] = i;
+		st.pair_row.push_back(p_in ? p_in[i] : i);
+		st.pair_col.push_back(h_pinv[i]);
+	}
+	for (int i = 0; i < n; i++)
+		if (h_pinv[i] < 0)
+			p[k++] = i;
+	st.pub.ms_pivots += timer.stop_ms();
+	return npiv;
+}
+
+/* ------------------------------------------------------------------ Schur complements */
+
+/* reference: src/spasm_schur.c:11-44.  rand() is called exactly R times, like the reference. */
+double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R)
+{
+	if (n == 0)
+		return 0;
+	std::vector<int> rows(R);
+	for (int t = 0; t < R; t++)
+		rows[t] = p[rand() % n];
+	DevBuf<int> d_rows;
+	d_rows.upload(rows.data(), rows.size(), ctx().stream);
+	E.solve_rows(A, d_rows.ptr, R, false);
+	i64 nnz = panel_count_nonzero(E.panel, E.Uqinv.ptr);
+	return ((double) nnz) / (E.m - E.U.n) / R;
+}
+
+/* reference: src/spasm_schur.c:61-193.  Rows come out in p order (the reference with one thread);
+ * entries of a row by increasing column. */
+void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
+{
+	cudaStream_t s = ctx().stream;
+	const int cap = panel_capacity(E.m);
+	struct Piece { DevBuf<i64> p; DevBuf<int> j; DevBuf<i32> x; i64 nnz; int rows; };
+	std::vector<Piece> pieces;
+	i64 total = 0;
+	for (int done = 0; done < n; done += cap) {
+		int R = std::min(cap, n - done);
+		DevBuf<int> d_rows;
+		d_rows.upload(p + done, (size_t) R, s);
+		E.solve_rows(A, d_rows.ptr, R, false);
+		Piece pc;
+		pc.rows = R;
+		panel_to_csr(E.panel, E.Uqinv.ptr, nullptr, 0, nullptr, pc.p, pc.j, pc.x, pc.nnz);
+		total += pc.nnz;
+		pieces.push_back(std::move(pc));
+	}
+	S.n = n;
+	S.m = E.m;
+	S.prime = E.prime;
+	S.nnz = total;
+	S.p.alloc((size_t) n + 1);
+	S.j.alloc((size_t) std::max<i64>(total, 1));
+	S.x.alloc((size_t) std::max<i64>(total, 1));
+	CUDA_CHECK(cudaMemsetAsync(S.p.ptr, 0, sizeof(i64), s));
+	i64 off = 0;
+	int row = 0;
+	for (Piece &pc : pieces) {
+		if (off)
+			k_add_offset<<<cdiv(pc.rows + 1, 256), 256, 0, s>>>(pc.p.ptr, pc.rows + 1, off);
+		CUDA_CHECK(cudaMemcpyAsync(S.p.ptr + row, pc.p.ptr, ((size_t) pc.rows + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+		if (pc.nnz) {
+			CUDA_CHECK(cudaMemcpyAsync(S.j.ptr + off, pc.j.ptr, (size_t) pc.nnz * sizeof(int), cudaMemcpyDeviceToDevice, s));
+			CUDA_CHECK(cudaMemcpyAsync(S.x.ptr + off, pc.x.ptr, (size_t) pc.nnz * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+		}
+		off += pc.nnz;
+		row += pc.rows;
+	}
+	sync();
+}
+
+/* ------------------------------------------------------------------ finishing strategies */
+
+static void record_block(int Sn, int Sm, int rr, int w)
+{
+	Stats &st = stats();
+	int k = st.pub.nblocks;
+	if (k < 4096) {
+		st.pub.block_Sn[k] = Sn;
+		st.pub.block_Sm[k] = Sm;
+		st.pub.block_rr[k] = rr;
+		st.pub.block_w[k] = w;
+	}
+	st.pub.nblocks = k + 1;
+}
+
+/* N random combinations of the rows p[0:n] of A, reduced by the structural rows, as a dense N x Sm0 block.
+ * Host side: the row choices (glibc rand(), k-major) and the coefficients (SHA-256 PRNG seeded with
+ * (prime, k, 0)) of the reference, spasm_schur.c:367-386. */
+static void randomized_block(Engine &E, const DevCsr &A, const int *p, int n, int N, int w, DevBuf<i32> &B, int &ldB)
+{
+	cudaStream_t s = ctx().stream;
+	int ww = (w <= 0) ? n : w;
+	std::vector<int> rows((size_t) N * ww);
+	std::vector<i32> coef((size_t) N * ww);
+	for (int k = 0; k < N; k++) {
+		spasm_prng_ctx prng;
+		spasm_prng_seed_simple(E.prime, (u64) k, 0, &prng);
+		if (w <= 0) {
+			for (int i = 0; i < n; i++) {
+				rows[(size_t) k * ww + i] = p[i];
+				coef[(size_t) k * ww + i] = spasm_prng_ZZp(&prng);
+			}
+		} else {
+			for (int t = 0; t < w; t++) {
+				rows[(size_t) k * ww + t] = p[rand() % n];
+				coef[(size_t) k * ww + t] = (t == 0) ? 1 : spasm_prng_ZZp(&prng);
+			}
+		}
+	}
+	DevBuf<int> d_rows;
+	DevBuf<i32> d_coef;
+	d_rows.upload(rows.data(), rows.size(), s);
+	d_coef.upload(coef.data(), coef.size(), s);
+	stats().pub.h2d_bytes += (i64) rows.size() * 8;
+	E.solve_combos(A, d_rows.ptr, d_coef.ptr, N, ww);
+	ldB = (E.Sm0 + 3) & ~3;
+	B.ensure((size_t) N * std::max(ldB, 4));
+	E.gather_q0(B.ptr, ldB);
+}
+
+/* reference: src/spasm_echelonize.c:30-51 */
+static bool test_completion(Engine &E, const DevCsr &A, const int *p, int n)
+{
+	if (n == 0 || A.nnz == 0)
+		return true;
+	int Sm = E.m - E.rank();
+	int Sn = (int) ceil(128 / log2((double) E.prime));
+	LOG("[echelonize/completion] Testing completion with %d random linear combinations (rank %d)\n", Sn, E.rank());
+	DevBuf<i32> B;
+	int ldB;
+	randomized_block(E, A, p, n, Sn, 0, B, ldB);
+	/* rank of the block after reduction by everything found so far: absorb on a scratch engine state */
+	size_t before = E.blocks.size();
+	int rank_before = E.dense_rank;
+	int rr = E.absorb_block(B.ptr, Sn, ldB);
+	/* the reference discards these rows (it only looks at rr) */
+	while (E.blocks.size() > before)
+		E.blocks.pop_back();
+	E.dense_rank = rank_before;
+	record_block(Sn, Sm, rr, 0);
+	return rr == 0;
+}
+
+/* reference: src/spasm_echelonize.c:315-379 */
+static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+{
+	E.begin_dense();
+	int Sm = E.m - E.rank();
+	LOG("[echelonize/dense/low-rank] processing dense schur complement of dimension %d x %d; block size=%d\n", n, Sm, opts->dense_block_size);
+	int rank_ub = spasm_min(n, Sm);
+	int w = (opts->low_rank_start_weight < 0) ? (int) ceil(-log(0.01) * n / rank_ub) : (int) opts->low_rank_start_weight;
+	DevBuf<i32> B;
+	int round = 0;
+	for (;;) {
+		int Sn = spasm_min(rank_ub, opts->dense_block_size);
+		if (Sn <= 0)
+			break;
+		LOG("[echelonize/dense/low-rank] Round %d. Weight %d. Processing chunk (%d x %d)\n", round, w, Sn, Sm);
+		int ldB;
+		randomized_block(E, A, p, n, Sn, w, B, ldB);
+		int rr = E.absorb_block(B.ptr, Sn, ldB);
+		record_block(Sn, Sm, rr, w);
+		if (rr == 0) {
+			if (test_completion(E, A, p, n))
+				break;
+			LOG("[echelonize/dense/low-rank] Failed termination test; switching to full linear combinations\n");
+			w = 0;
+			Sn = 1;          /* the reference stores omp_get_max_threads(); only the comparison below reads it */
+		}
+		if (rr < 0.9 * Sn) {
+			w *= 2;
+			LOG("[echelonize/dense/low-rank] Not enough pivots, increasing weight to %d\n", w);
+		}
+		n -= rr;             /* sic (echelonize.c:369): the sampling range shrinks */
+		Sm -= rr;
+		rank_ub -= rr;
+		round += 1;
+		LOG("[echelonize/dense/low-rank] found %d new pivots\n", rr);
+	}
+}
+
+/* reference: src/spasm_echelonize.c:385-463 */
+static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+{
+	E.begin_dense();
+	cudaStream_t s = ctx().stream;
+	int Sm = E.m - E.rank();
+	LOG("[echelonize/dense] processing dense schur complement of dimension %d x %d; block size=%d\n", n, Sm, opts->dense_block_size);
+	int processed = 0, round = 0;
+	bool lowrank_mode = false;
+	int rank_ub = spasm_min(A.n - E.rank(), A.m - E.rank());
+	DevBuf<i32> B;
+	for (;;) {
+		int Sn = spasm_min(opts->dense_block_size, n - processed);
+		if (Sn <= 0)
+			break;
+		LOG("[echelonize/dense] Round %d. processing S[%d:%d] (%d x %d)\n", round, processed, processed + Sn, Sn, Sm);
+		DevBuf<int> d_rows;
+		d_rows.upload(p, (size_t) Sn, s);
+		E.solve_rows(A, d_rows.ptr, Sn, false);
+		int ldB = (E.Sm0 + 3) & ~3;
+		B.ensure((size_t) Sn * std::max(ldB, 4));
+		E.gather_q0(B.ptr, ldB);
+		int rr = E.absorb_block(B.ptr, Sn, ldB);
+		record_block(Sn, Sm, rr, -1);
+		round += 1;
+		processed += Sn;
+		p += Sn;
+		Sm = E.m - E.rank();
+		rank_ub = spasm_min(A.n - E.rank(), A.m - E.rank());
+		LOG("[echelonize/dense] found %d new pivots\n", rr);
+		if (opts->enable_tall_and_skinny && (rr < opts->low_rank_ratio * Sn)) {
+			lowrank_mode = true;
+			break;
+		}
+	}
+	if (rank_ub > 0 && n - processed > 0 && lowrank_mode) {
+		LOG("[echelonize/dense] Too few pivots; switching to low-rank mode\n");
+		finish_lowrank(E, A, p, n - processed, opts);
+	}
+}
+
+/* ------------------------------------------------------------------ result assembly */
+
+/* copy the echelon form to malloc'ed host memory: structural rows, then the dense rows in the
+ * order they were found (reference: update_U_after_rref, echelonize.c:192-223) */
+static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
+{
+	cudaStream_t s = ctx().stream;
+	struct Piece { DevBuf<i64> p; DevBuf<int> j; DevBuf<i32> x; i64 nnz; int rows; };
+	std::vector<Piece> pieces;
+	i64 total = E.U.nnz;
+	for (DenseBlock &blk : E.blocks) {
+		Piece pc;
+		pc.rows = blk.rr;
+		dense_rows_to_csr(blk.D.ptr, blk.ld, blk.rr, E.Sm0, blk.d_pivcol.ptr, blk.d_own.ptr, E.d_q0.ptr, pc.p, pc.j, pc.x, pc.nnz);
+		total += pc.nnz;
+		pieces.push_back(std::move(pc));
+	}
+	int rank = E.rank();
+	struct spasm_csr *U = spasm_csr_alloc(std::max(rank, n_rows_alloc), E.m, std::max<i64>(total, 1), E.prime, true);
+	int *qinv = (int *) spasm_malloc((i64) std::max(E.m, 1) * sizeof(int));
+	E.U.p.download(U->p, (size_t) E.U.n + 1, s);
+	E.U.j.download(U->j, (size_t) E.U.nnz, s);
+	E.U.x.download(U->x, (size_t) E.U.nnz, s);
+	E.Uqinv.download(qinv, (size_t) E.m, s);
+	sync();
+	i64 off = E.U.nnz;
+	int row = E.U.n;
+	for (size_t b = 0; b < pieces.size(); b++) {
+		Piece &pc = pieces[b];
+		std::vector<i64> hp((size_t) pc.rows + 1);
+		pc.p.download(hp.data(), hp.size(), s);
+		pc.j.download(U->j + off, (size_t) pc.nnz, s);
+		pc.x.download(U->x + off, (size_t) pc.nnz, s);
+		sync();
+		for (int t = 0; t < pc.rows; t++) {
+			U->p[row + t + 1] = off + hp[t + 1];
+			qinv[E.q0[E.blocks[b].pivcol[t]]] = row + t;
+		}
+		off += pc.nnz;
+		row += pc.rows;
+	}
+	stats().pub.d2h_bytes += total * 8 + (i64) (rank + 1) * 8 + (i64) E.m * 4;
+	U->n = rank;
+	/* trim like the reference does (echelonize.c:603-604) */
+	spasm_csr_resize(U, rank, E.m);
+	spasm_csr_realloc(U, -1);
+	struct spasm_lu *fact = (struct spasm_lu *) spasm_malloc(sizeof(*fact));
+	fact->r = rank;
+	fact->complete = false;
+	fact->L = NULL;
+	fact->U = U;
+	fact->qinv = qinv;
+	fact->p = NULL;
+	fact->Ltmp = NULL;
+	return fact;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+/* ================================================================== C ABI */
+
+extern "C" {
+
+/* reference: src/spasm_echelonize.c:9-28 */
+void spasm_echelonize_init_opts(struct echelonize_opts *opts)
+{
+	opts->enable_greedy_pivot_search = 1;
+	opts->enable_tall_and_skinny = 1;
+	opts->enable_dense = 1;
+	opts->enable_GPLU = 1;
+	opts->L = 0;
+	opts->complete = 0;
+	opts->min_pivot_proportion = 0.1;
+	opts->max_round = 3;
+	opts->sparsity_threshold = 0.05;
+	opts->tall_and_skinny_ratio = 5;
+	opts->dense_block_size = 1000;
+	opts->low_rank_ratio = 0.5;
+	opts->low_rank_start_weight = -1;
+}
+
+/* reference: src/spasm_echelonize.c:473-617 */
+struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts)
+{
+	struct echelonize_opts default_opts;
+	if (opts == NULL) {
+		LOG("[echelonize] using default settings\n");
+		opts = &default_opts;
+		spasm_echelonize_init_opts(opts);
+	}
+	double start = spasm_wtime();
+	Stats &st = stats();
+	st.pair_row.clear();
+	st.pair_col.clear();
+	st.pair_start.assign(1, 0);
+	st.pub.nrounds = 0;
+	st.pub.nblocks = 0;
+	st.pub.finish = 0;
+	int n = A->n, m = A->m;
+	i64 prime = spasm_get_prime(A);
+	LOG("[echelonize] Start on %d x %d matrix with %" PRId64 " nnz\n", n, m, spasm_nnz(A));
+	if (opts->complete)
+		opts->L = 1;
+	if (opts->L)
+		errx(1, "[spasm-b200] opts->L / opts->complete (PLUQ with L) is not part of the B200 echelonization path (DESIGN.md, out of scope)");
+	if (opts->dense_block_size <= 0)
+		errx(1, "[spasm-b200] dense_block_size must be positive");
+
+	ctx();
+	Engine E;
+	E.init(m, prime);
+	DevCsr dA0;
+	dA0.upload(A);
+	DevCsr dS;                       /* current Schur complement once a round has run */
+	const DevCsr *cur = &dA0;
+
+	std::vector<int> p((size_t) std::max(n, 1));
+	std::vector<int> p_in;           /* empty = identity */
+	double density = (double) spasm_nnz(A) / n / m;
+	int npiv = 0, status = 0, round;
+	for (round = 0; round < opts->max_round; round++) {
+		if (cur->nnz == 0) {
+			LOG("[echelonize] empty matrix\n");
+			status = 1;
+			break;
+		}
+		LOG("[echelonize] round %d\n", round);
+		npiv = extract_structural(E, *cur, p_in.empty() ? NULL : p_in.data(), p.data(), opts->enable_greedy_pivot_search, round);
+		st.pub.nrounds = round + 1;
+		st.pair_start.push_back((int) st.pair_row.size());
+		if (npiv < opts->min_pivot_proportion * spasm_min(n, m - E.U.n)) {
+			LOG("[echelonize] not enough pivots found; stopping\n");
+			status = 2;
+			break;
+		}
+		density = estimate_density(E, *cur, p.data() + npiv, n - npiv, 100);
+		if (round < 64)
+			st.pub.density[round] = density;
+		if (density > opts->sparsity_threshold) {
+			LOG("[echelonize] Schur complement is dense (estimated %.2f%%)\n", 100 * density);
+			status = 2;
+			break;
+		}
+		LOG("Schur complement is %d x %d, estimated density : %.2f\n", n - npiv, m - E.U.n, density);
+		DevCsr S;
+		schur_sparse(E, *cur, p.data() + npiv, n - npiv, S);
+		std::vector<int> p_out((size_t) (n - npiv));
+		for (int k = 0; k < n - npiv; k++) {
+			int row = p[npiv + k];
+			p_out[k] = p_in.empty() ? row : p_in[row];
+		}
+		LOG("Schur complement: %d * %d [%" PRId64 " nz / density= %.3f]\n", n - npiv, m, S.nnz, 1.0 * S.nnz / (1.0 * m * (n - npiv)));
+		dS = std::move(S);
+		cur = &dS;
+		n = n - npiv;
+		p_in = std::move(p_out);
+		if (p_in.empty())
+			p_in.push_back(0);           /* keep "non-empty == not the identity" even for zero rows */
+	}
+	if (status == 0) {
+		npiv = 0;
+		for (int i = 0; i < n; i++)
+			p[i] = i;
+	}
+	if (status != 1) {
+		if (!opts->enable_tall_and_skinny)
+			LOG("[echelonize] dense low-rank mode disabled\n");
+		if (!opts->enable_dense)
+			LOG("[echelonize] regular dense mode disabled\n");
+		if (!opts->enable_GPLU)
+			LOG("[echelonize] GPLU mode disabled\n");
+		double aspect_ratio = (double) (n - npiv) / (m - E.U.n);
+		LOG("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
+		if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio) {
+			st.pub.finish = 1;
+			finish_lowrank(E, *cur, p.data() + npiv, n - npiv, opts);
+		} else if (opts->enable_dense && density > opts->sparsity_threshold) {
+			st.pub.finish = 2;
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, opts);
+		} else if (opts->enable_GPLU) {
+			/* The reference finishes row by row (echelonize_GPLU, echelonize.c:54-187): leftmost pivot of each
+			 * reduced row.  That rule selects the column rank profile of the Schur complement, which is what
+			 * the dense echelon form selects too, so the canonical result (rank, pivot columns, RREF, kernel)
+			 * is the same; here it is computed block-wise on the GPU.  (a sequential GPU GPLU
+			 * is a later row.)  No low-rank switch: GPLU processes every row. */
+			st.pub.finish = 3;
+			struct echelonize_opts o2 = *opts;
+			o2.enable_tall_and_skinny = 0;
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2);
+		} else {
+			LOG("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
+		}
+	}
+	struct spasm_lu *fact = assemble(E, 0);
+	st.pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
+	LOG("[echelonize] Done in %.3fs. Rank %d, %" PRId64 " nz in basis\n", spasm_wtime() - start, fact->U->n, spasm_nnz(fact->U));
+	return fact;
+}
+
+}  /* extern "C" */

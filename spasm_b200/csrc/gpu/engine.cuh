@@ -1,0 +1,58 @@
+/*
+ * Device-resident state shared by the drivers (echelonize.cu, api.cu):
+ * an echelon form under construction = structural sparse rows U (CSR on the
+ * device) + its solve schedule + the dense rows produced by the dense phases.
+ */
+#pragma once
+#include "common.cuh"
+#include "dense.cuh"
+#include "panel.cuh"
+#include "pivots.cuh"
+#include "solve.cuh"
+#include "zp.cuh"
+
+namespace sb {
+
+/* one batch of rows produced by a dense echelonization: rr RREF rows over the q0 column space */
+struct DenseBlock {
+	int rr = 0;
+	DevBuf<i32> D;                   /* rr x Sm0, row-major, leading dimension ld */
+	int ld = 0;
+	std::vector<int> pivcol;         /* pivot column (index into q0) of each row, increasing */
+	DevBuf<int> d_pivcol;
+	DevBuf<unsigned char> d_own;     /* flag per q0 column: pivot of this block */
+};
+
+struct Engine {
+	int m = 0;
+	i64 prime = 0;
+	Zp F;
+	/* structural part */
+	DevCsr U;
+	DevBuf<int> Uqinv;               /* size m; row of U (structural index) or -1 */
+	DepGraph G;                      /* forward dependency graph of U, scheduled */
+	bool G_ready = false;
+	/* dense part, over the columns that are non-pivotal after the structural rounds */
+	bool dense_ready = false;
+	int Sm0 = 0;
+	std::vector<int> q0;             /* q0[c] = column of A */
+	DevBuf<int> d_q0;
+	std::vector<DenseBlock> blocks;
+	int dense_rank = 0;
+	Panel panel;
+
+	void init(int m_, i64 prime_);
+	void rebuild_schedule();                         /* G from U */
+	void begin_dense();                              /* freeze q0 */
+	int rank() const { return U.n + dense_rank; }
+
+	/* solve the rows `rows` (indices into B) against the structural U: results in panel */
+	void solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first);
+	void solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w);
+	/* gather the q0 columns of the panel into a dense row-major block (R x Sm0, ld = ldS) */
+	void gather_q0(i32 *S, int ldS);
+	/* reduce a dense block by the dense rows found so far, echelonize it, keep its pivot rows. Returns rr. */
+	int absorb_block(i32 *B, int rows, int ldB);
+};
+
+}  // namespace sb

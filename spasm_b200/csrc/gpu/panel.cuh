@@ -1,0 +1,39 @@
+/*
+ * Right-hand-side panels for the batched solve: building them from sparse rows
+ * (or random combinations of rows) and reading results back out.
+ * Layout in HBM: X[node][r], one vector of `ld` int32 per node (column of the
+ * matrix), r = index of the right-hand side inside the batch, ld % 4 == 0.
+ */
+#pragma once
+#include "common.cuh"
+#include "zp.cuh"
+
+namespace sb {
+
+struct Panel {
+	DevBuf<i32> X;
+	int nnodes = 0, ld = 0, R = 0;
+	void shape(int nnodes_, int R_);     /* (re)allocate and zero */
+};
+
+/* how many right-hand sides fit the panel budget for this many nodes */
+int panel_capacity(int nnodes);
+
+/* X[B.j[e]][r] += B.x[e] for every entry e of row rows[r] (r < R); skip_first drops the first entry of each row */
+void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first);
+/* X[.][k] += coef[k*w+t] * A[rows[k*w+t]]   for k < N, t < w */
+void panel_scatter_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, Panel &P, const Zp &F);
+/* transposed variant for spasm_kernel: right-hand side r = column cols[r] of U, i.e. X[i][r] = U[i][cols[r]] */
+void panel_scatter_columns(const DevCsr &U, const int *d_colslot /* size m: slot of a column or -1 */, Panel &P);
+
+/* S[r*ldS + c] = X[q[c]][r]  (row-major dense block, reference: src/spasm_schur.c:205-233 "gather") */
+void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS);
+/* number of non-zero entries on nodes with flag[node] < 0 (non-pivotal columns) over the whole panel */
+i64 panel_count_nonzero(const Panel &P, const int *d_flag);
+
+/* CSR of the panel restricted to nodes with flag[node] < 0, entries of a row by increasing node.
+ * If d_first != NULL, row r starts with the extra entry (first_col[r], first_val) (used by rref / kernel). */
+void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32 first_val, const int *d_node_to_col,
+                  DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, i64 &nnz);
+
+}  // namespace sb

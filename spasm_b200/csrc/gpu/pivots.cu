@@ -1,0 +1,608 @@
+/*
+ * Structural pivot search on the GPU (reference: src/spasm_pivots.c).
+ *
+ * The three searches of the reference are sequential scans whose result depends
+ * on the order in which rows are visited.  Each kernel family below computes
+ * exactly the result of the reference run with ONE thread (rows in increasing
+ * order), with a parallel schedule:
+ *
+ *  - Faugere-Lachartre (pivots.c:41-66): per column, the row whose leftmost entry
+ *    is that column, of minimum weight, lowest index on ties  ==  a 64-bit
+ *    atomicMin on (weight, row) keys.
+ *  - FL on columns (pivots.c:76-122): a lexicographically-first greedy.  Rounds of
+ *    "deterministic reservations": every undecided row reserves its open columns
+ *    with atomicMin(row index); a row whose open columns are all reserved by
+ *    itself can decide now (no lower row can close any of them); it takes its
+ *    first open entry and closes its columns.  The lowest undecided row always
+ *    decides, so the rounds terminate, and the outcome is the sequential one.
+ *  - greedy alternating-cycle-free search (pivots.c:146-294): the reference's own
+ *    transactional scheme (journal of new pivots, replay on commit failure), with
+ *    the commit section taken in increasing row order.  Each CTA owns one
+ *    candidate row at a time, runs the BFS with a visited bitmap in shared memory
+ *    against the live pivot set, and when it holds a survivor waits until every
+ *    lower row is resolved, replays the journal entries it has not seen
+ *    (pivots.c:260-274) and commits.  Rows that exhaust their survivors are
+ *    resolved at once: reachability only grows with the pivot set.
+ *
+ * Pivotal rows are then ordered by the levels of the pivot DAG (a valid
+ * triangular order; the reference uses a DFS order, pivots.c:325-362 -- the row
+ * order inside U is not part of the canonical result) and copied
+ * to U with the pivot first and scaled to 1 (pivots.c:405-443).
+ */
+#include <cub/cub.cuh>
+#include "pivots.cuh"
+#include "stats.cuh"
+
+namespace sb {
+
+/* ============================================================ Faugere-Lachartre */
+
+__global__ void k_fl_keys(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, unsigned long long *key)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	i64 b = Ap[i], e = Ap[i + 1];
+	if (b == e)
+		return;
+	int lead = Aj[b];
+	for (i64 k = b + 1; k < e; k++)
+		lead = min(lead, Aj[k]);
+	unsigned long long mine = ((unsigned long long) (e - b) << 32) | (unsigned) i;
+	atomicMin(&key[lead], mine);
+}
+
+__global__ void k_fl_assign(int m, const unsigned long long *__restrict__ key, int *pinv, int *qinv, int *count)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m)
+		return;
+	unsigned long long k = key[j];
+	if (k == ~0ull)
+		return;
+	int i = (int) (k & 0xffffffffull);
+	qinv[j] = i;
+	pinv[i] = j;
+	atomicAdd(count, 1);
+}
+
+/* ============================================================ FL on columns */
+
+__global__ void k_flc_close_pivotal(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ pinv,
+                                    unsigned char *open, unsigned char *decided)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	if (pinv[i] >= 0) {
+		decided[i] = 1;
+		for (i64 k = Ap[i]; k < Ap[i + 1]; k++)
+			open[Aj[k]] = 0;
+	}
+}
+
+/* undecided rows reserve their open columns; rows without any are decided (no pivot) */
+__global__ void k_flc_reserve(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ qinv,
+                              const unsigned char *__restrict__ open, unsigned char *decided, int *minrow, int *undecided)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || decided[i])
+		return;
+	bool any = false;
+	for (i64 k = Ap[i]; k < Ap[i + 1]; k++) {
+		int j = Aj[k];
+		if (open[j]) {              /* an open column is never pivotal: pivot columns lie in a pivotal row, all of which are closed */
+			any = true;
+			atomicMin(&minrow[j], i);
+		}
+	}
+	if (!any)
+		decided[i] = 1;
+	else
+		atomicAdd(undecided, 1);
+}
+
+__global__ void k_flc_commit(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, int *pinv, int *qinv,
+                             const unsigned char *__restrict__ open, unsigned char *decided, const int *__restrict__ minrow,
+                             unsigned char *closing, int *count)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || decided[i])
+		return;
+	int first = -1;
+	for (i64 k = Ap[i]; k < Ap[i + 1]; k++) {
+		int j = Aj[k];
+		if (open[j]) {              /* open[] is not written by this kernel: every row sees the same snapshot */
+			if (minrow[j] != i)
+				return;            /* a lower undecided row may still close this column */
+			if (first < 0)
+				first = j;
+		}
+	}
+	/* safe: the open columns of this row are disjoint from those of every other safe row, so the
+	 * writes below cannot conflict (qinv[first] is read by no other committing row) */
+	qinv[first] = i;
+	pinv[i] = first;
+	decided[i] = 1;
+	closing[i] = 1;
+	atomicAdd(count, 1);
+}
+
+__global__ void k_flc_close(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, unsigned char *closing, unsigned char *open)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !closing[i])
+		return;
+	closing[i] = 0;
+	for (i64 k = Ap[i]; k < Ap[i + 1]; k++)
+		open[Aj[k]] = 0;
+}
+
+/* ============================================================ greedy cycle-free search */
+
+struct GreedyArgs {
+	int n, m, words, queue_cap, use_smem;
+	const i64 *Ap;
+	const int *Aj;
+	int *qinv, *pinv;
+	int *journal;
+	int *npiv;       /* committed pivots (journal length) */
+	int *found;      /* sum of register_pivot results */
+	int *ticket;
+	int *status;     /* per row: 1 once resolved */
+	int *hint;       /* every row below *hint is resolved */
+	unsigned *bitmaps;
+	int *queues;
+	unsigned long long *edges;
+};
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
+
+struct GreedyShared {
+	int row, head, tail, alive, npiv_local, scan, replayed;
+};
+
+__device__ __forceinline__ void greedy_mark(int c, unsigned *vis, unsigned *srv, int *queue, GreedyShared *sh)
+{
+	unsigned bit = 1u << (c & 31);
+	int word = c >> 5;
+	unsigned old = atomicOr(&vis[word], bit);
+	if (old & bit)
+		return;
+	unsigned olds = atomicAnd(&srv[word], ~bit);
+	if (olds & bit)
+		atomicSub(&sh->alive, 1);
+	queue[atomicAdd(&sh->tail, 1)] = c;
+}
+
+__global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
+{
+	extern __shared__ unsigned dyn_smem[];
+	__shared__ GreedyShared sh;
+	const int tid = threadIdx.x, T = blockDim.x;
+	unsigned *vis = a.use_smem ? dyn_smem : a.bitmaps + (size_t) blockIdx.x * 2 * a.words;
+	unsigned *srv = vis + a.words;
+	int *queue = a.queues + (size_t) blockIdx.x * a.queue_cap;
+	unsigned long long my_edges = 0;
+
+	for (int w = tid; w < 2 * a.words; w += T)
+		vis[w] = 0;
+	if (tid == 0)
+		sh.scan = 0;
+	__syncthreads();
+
+	for (;;) {
+		if (tid == 0)
+			sh.row = atomicAdd(a.ticket, 1);
+		__syncthreads();
+		const int i = sh.row;
+		if (i >= a.n)
+			break;
+		if (ld_volatile(&a.pinv[i]) >= 0) {        /* already pivotal (pivots.c:192) */
+			if (tid == 0) {
+				__threadfence();
+				*((volatile int *) &a.status[i]) = 1;
+			}
+			__syncthreads();
+			continue;
+		}
+		const i64 rb = a.Ap[i], re = a.Ap[i + 1];
+
+		/* ---- begin the transaction: read the journal length, then scatter the row (pivots.c:198-215).
+		 * Done by one thread in entry order: with a repeated column the count `alive` follows the
+		 * reference's arithmetic (alive -= w[j]) exactly. */
+		if (tid == 0) {
+			int np = ld_volatile(a.npiv);
+			__threadfence();
+			sh.npiv_local = np;
+			int tail = 0, alive = 0;
+			for (i64 k = rb; k < re; k++) {
+				int j = a.Aj[k];
+				unsigned bit = 1u << (j & 31);
+				int word = j >> 5;
+				if (ld_volatile(&a.qinv[j]) < 0) {
+					srv[word] |= bit;
+					alive += 1;
+				} else {
+					int wj = (srv[word] & bit) ? 1 : ((vis[word] & bit) ? -1 : 0);
+					queue[tail++] = j;
+					alive -= wj;
+					vis[word] |= bit;
+					srv[word] &= ~bit;
+				}
+			}
+			sh.head = 0;
+			sh.tail = tail;
+			sh.alive = alive;
+			sh.replayed = 0;
+		}
+		__syncthreads();
+
+		bool my_turn = false;
+		for (;;) {
+			/* ---- BFS along alternating paths (pivots.c:218-225), one frontier slice per iteration */
+			for (;;) {
+				const int head = sh.head, tail = sh.tail, alive = sh.alive;
+				__syncthreads();
+				if (head >= tail || alive <= 0)
+					break;
+				const int cnt = min(T, tail - head);
+				if (tid < cnt) {
+					int j = queue[head + tid];
+					int I = ld_volatile(&a.qinv[j]);
+					if (I >= 0) {
+						i64 b = a.Ap[I], e = a.Ap[I + 1];
+						for (i64 k = b; k < e; k++)
+							greedy_mark(a.Aj[k], vis, srv, queue, &sh);
+						my_edges += (unsigned long long) (e - b);
+					}
+				}
+				if (tid == 0)
+					sh.head = head + cnt;
+				__syncthreads();
+			}
+			if (sh.alive <= 0)
+				break;                          /* no survivor: final, whatever happens later */
+			if (!my_turn) {
+				/* ---- wait until every lower row is resolved: from here on nobody else commits */
+				if (tid == 0) {
+					int k = max(sh.scan, ld_volatile(a.hint));
+					while (k < i) {
+						if (ld_volatile(&a.status[k]))
+							k++;
+						else
+							__nanosleep(100);
+					}
+					__threadfence();
+					sh.scan = k;
+				}
+				__syncthreads();
+				my_turn = true;
+			}
+			/* ---- replay the pivots committed since the transaction began (pivots.c:260-274) */
+			const int np_now = ld_volatile(a.npiv);
+			const int np_old = sh.npiv_local;
+			__syncthreads();
+			if (np_now == np_old)
+				break;                          /* state is exact: commit */
+			for (int t = np_old + tid; t < np_now; t += T) {
+				int j = ld_volatile(&a.journal[t]);
+				unsigned bit = 1u << (j & 31);
+				int word = j >> 5;
+				if (srv[word] & bit) {          /* a survivor became pivotal */
+					unsigned olds = atomicAnd(&srv[word], ~bit);
+					if (olds & bit) {
+						atomicSub(&sh.alive, 1);
+						atomicOr(&vis[word], bit);
+						queue[atomicAdd(&sh.tail, 1)] = j;
+					}
+				} else if (vis[word] & bit) {   /* a reached column became pivotal: expand its row */
+					int I = ld_volatile(&a.qinv[j]);
+					i64 b = a.Ap[I], e = a.Ap[I + 1];
+					for (i64 k = b; k < e; k++)
+						greedy_mark(a.Aj[k], vis, srv, queue, &sh);
+					my_edges += (unsigned long long) (e - b);
+				}
+			}
+			if (tid == 0)
+				sh.npiv_local = np_now;
+			__syncthreads();
+		}
+
+		/* ---- commit (pivots.c:227-255) */
+		if (tid == 0) {
+			if (sh.alive > 0) {
+				int j = -1;
+				for (i64 k = rb; k < re; k++) {     /* first survivor in row order; the last entry if none (quirk, see oracle) */
+					j = a.Aj[k];
+					if (srv[j >> 5] & (1u << (j & 31)))
+						break;
+				}
+				int result = 1;
+				int oldrow = ld_volatile(&a.qinv[j]);
+				if (oldrow != -1) {                  /* only reachable through rows with a repeated column */
+					a.pinv[oldrow] = -1;
+					result = 0;
+				}
+				a.pinv[i] = j;
+				*((volatile int *) &a.qinv[j]) = i;
+				int np = ld_volatile(a.npiv);
+				a.journal[np] = j;
+				__threadfence();
+				if (result) {
+					*((volatile int *) a.npiv) = np + 1;
+					atomicAdd(a.found, 1);
+				}
+			}
+			__threadfence();
+			*((volatile int *) &a.status[i]) = 1;
+			if (my_turn)
+				atomicMax(a.hint, i + 1);      /* every row up to i is resolved */
+		}
+		__syncthreads();
+
+		/* ---- reset the bitmaps (pivots.c:276-285) */
+		for (i64 k = rb + tid; k < re; k += T) {
+			int j = a.Aj[k];
+			atomicAnd(&vis[j >> 5], ~(1u << (j & 31)));
+			atomicAnd(&srv[j >> 5], ~(1u << (j & 31)));
+		}
+		const int tail = sh.tail;
+		for (int t = tid; t < tail; t += T) {
+			int j = queue[t];
+			atomicAnd(&vis[j >> 5], ~(1u << (j & 31)));
+		}
+		__syncthreads();
+	}
+	if (my_edges)
+		atomicAdd(a.edges, my_edges);
+}
+
+/* rows holding the same column twice (possible only through the compress quirk) */
+__global__ void k_row_keys(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, unsigned long long *keys)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (int i = warp; i < n; i += nwarps)
+		for (i64 k = Ap[i] + lane; k < Ap[i + 1]; k += 32)
+			keys[k] = ((unsigned long long) (unsigned) i << 32) | (unsigned) Aj[k];
+}
+
+__global__ void k_adjacent_equal(i64 nnz, const unsigned long long *__restrict__ keys, int *flag)
+{
+	i64 k = (i64) blockIdx.x * blockDim.x + threadIdx.x;
+	if (k + 1 < nnz && keys[k] == keys[k + 1])
+		*flag = 1;
+}
+
+static bool has_repeated_columns(const DevCsr &A)
+{
+	if (A.nnz < 2)
+		return false;
+	cudaStream_t s = ctx().stream;
+	DevBuf<unsigned long long> keys((size_t) A.nnz), sorted((size_t) A.nnz);
+	DevBuf<int> flag(1);
+	flag.zero(s);
+	k_row_keys<<<std::min(cdiv((size_t) A.n * 32, 256), 148u * 8), 256, 0, s>>>(A.n, A.p, A.j, keys.ptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.ptr, sorted.ptr, (int) A.nnz, 0, 64, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, sorted.ptr, (int) A.nnz, 0, 64, s);
+	k_adjacent_equal<<<cdiv((size_t) A.nnz, 256), 256, 0, s>>>(A.nnz, sorted.ptr, flag.ptr);
+	LAUNCHED(3);
+	KERNEL_CHECK();
+	return fetch(flag.ptr) != 0;
+}
+
+/* ============================================================ driver */
+
+PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
+{
+	cudaStream_t s = ctx().stream;
+	const int n = A.n, m = A.m;
+	PivotCounts out = {0, 0, 0};
+	CUDA_CHECK(cudaMemsetAsync(d_pinv, 0xff, (size_t) n * sizeof(int), s));
+	CUDA_CHECK(cudaMemsetAsync(d_qinv, 0xff, (size_t) m * sizeof(int), s));
+	if (n == 0 || m == 0 || A.nnz == 0)
+		return out;
+	DevBuf<int> counters(8);
+	counters.zero(s);
+
+	/* --- Faugere-Lachartre */
+	{
+		DevBuf<unsigned long long> key((size_t) m);
+		key.fill_byte(0xff, s);
+		k_fl_keys<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, key.ptr);
+		k_fl_assign<<<cdiv(m, 256), 256, 0, s>>>(m, key.ptr, d_pinv, d_qinv, counters.ptr + 0);
+		LAUNCHED(2);
+		KERNEL_CHECK();
+		out.fl = fetch(counters.ptr + 0);
+	}
+
+	/* --- FL on columns */
+	{
+		DevBuf<unsigned char> open((size_t) m), decided((size_t) n), closing((size_t) n);
+		DevBuf<int> minrow((size_t) m);
+		open.fill_byte(1, s);
+		decided.zero(s);
+		closing.zero(s);
+		k_flc_close_pivotal<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, d_pinv, open.ptr, decided.ptr);
+		LAUNCHED(1);
+		for (int round = 0;; round++) {
+			minrow.fill_byte(0x7f, s);
+			CUDA_CHECK(cudaMemsetAsync(counters.ptr + 1, 0, sizeof(int), s));
+			k_flc_reserve<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, d_qinv, open.ptr, decided.ptr, minrow.ptr, counters.ptr + 1);
+			LAUNCHED(1);
+			if (fetch(counters.ptr + 1) == 0)
+				break;
+			k_flc_commit<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, d_pinv, d_qinv, open.ptr, decided.ptr, minrow.ptr, closing.ptr, counters.ptr + 2);
+			k_flc_close<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, closing.ptr, open.ptr);
+			LAUNCHED(2);
+		}
+		KERNEL_CHECK();
+		out.flcol = fetch(counters.ptr + 2);
+	}
+
+	/* --- greedy */
+	if (greedy) {
+		GpuTimer timer;
+		timer.start();
+		bool sequential = has_repeated_columns(A);
+		GreedyArgs a;
+		a.n = n;
+		a.m = m;
+		a.words = (m + 31) / 32;
+		a.Ap = A.p;
+		a.Aj = A.j;
+		a.qinv = d_qinv;
+		a.pinv = d_pinv;
+		size_t bitmap_bytes = (size_t) 2 * a.words * sizeof(unsigned);
+		a.use_smem = bitmap_bytes <= 200 * 1024;
+		size_t smem = a.use_smem ? bitmap_bytes : 0;
+		if (smem > 0)
+			CUDA_CHECK(cudaFuncSetAttribute(k_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		int occ = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy, 256, smem));
+		if (occ < 1)
+			errx(1, "[spasm-b200] greedy pivot search kernel does not fit");
+		int blocks = sequential ? 1 : std::min(occ, 8) * ctx().sm_count;
+		blocks = std::min(blocks, std::max(1, n));
+		/* longest row bounds the extra queue slots used by the initial scatter */
+		a.queue_cap = m + 64;
+		{
+			/* rows longer than 64 entries: enlarge the queues by the longest row */
+			std::vector<i64> hp((size_t) n + 1);
+			A.p.download(hp.data(), (size_t) n + 1, s);
+			sync();
+			i64 longest = 0;
+			for (int i = 0; i < n; i++)
+				longest = std::max(longest, hp[i + 1] - hp[i]);
+			a.queue_cap = m + (int) longest + 64;
+		}
+		DevBuf<int> journal((size_t) n + 1), status((size_t) n + 1), queues((size_t) blocks * a.queue_cap);
+		DevBuf<unsigned> bitmaps(a.use_smem ? 1 : (size_t) blocks * 2 * a.words);
+		DevBuf<unsigned long long> edges(1);
+		status.zero(s);
+		edges.zero(s);
+		CUDA_CHECK(cudaMemsetAsync(counters.ptr + 3, 0, 4 * sizeof(int), s));
+		a.journal = journal.ptr;
+		a.npiv = counters.ptr + 3;
+		a.found = counters.ptr + 4;
+		a.ticket = counters.ptr + 5;
+		a.hint = counters.ptr + 6;
+		a.status = status.ptr;
+		a.bitmaps = bitmaps.ptr;
+		a.queues = queues.ptr;
+		a.edges = edges.ptr;
+		k_greedy<<<blocks, 256, smem, s>>>(a);
+		LAUNCHED(1);
+		KERNEL_CHECK();
+		out.greedy = fetch(counters.ptr + 4);
+		stats().pub.greedy_edges += (i64) fetch(edges.ptr);
+		stats().pub.ms_pivots_greedy += timer.stop_ms();
+	}
+	return out;
+}
+
+/* ============================================================ copy pivotal rows to U */
+
+__global__ void k_urow_len(int npiv, const int *__restrict__ rows, const i64 *__restrict__ Ap, const int *__restrict__ Aj,
+                           const int *__restrict__ pinv, i64 *len)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= npiv)
+		return;
+	int i = rows[k], j = pinv[i];
+	i64 c = 1;
+	for (i64 e = Ap[i]; e < Ap[i + 1]; e++)
+		c += (Aj[e] != j);
+	len[k] = c;
+}
+
+/* one warp per pivotal row: pivot first and equal to 1, the rest scaled by its inverse (pivots.c:405-443) */
+__global__ void k_urow_fill(int npiv, const int *__restrict__ rows, const i64 *__restrict__ Ap, const int *__restrict__ Aj,
+                            const i32 *__restrict__ Ax, const int *__restrict__ pinv, const i64 *__restrict__ Up_new, i64 unz0,
+                            int un0, i64 *Up, int *Uj, i32 *Ux, int *Uqinv, Zp F)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (int k = warp; k < npiv; k += nwarps) {
+		int i = rows[k], j = pinv[i];
+		i64 b = Ap[i], e = Ap[i + 1];
+		/* the pivot value: first entry on column j (pivots.c:413-419) */
+		i64 where = e;
+		for (i64 k0 = b; k0 < e && where == e; k0 += 32) {
+			i64 q = k0 + lane;
+			bool hit = (q < e) && (Aj[q] == j) && (Ax[q] != 0);
+			unsigned mask = __ballot_sync(0xffffffffu, hit);
+			if (mask)
+				where = k0 + (__ffs(mask) - 1);
+		}
+		i32 alpha = zp_inverse(Ax[where], F);
+		i64 out = unz0 + Up_new[k];
+		if (lane == 0) {
+			Uj[out] = j;
+			Ux[out] = 1;
+			Uqinv[j] = un0 + k;
+			Up[un0 + k + 1] = unz0 + Up_new[k + 1];
+		}
+		i64 written = 1;
+		for (i64 k0 = b; k0 < e; k0 += 32) {
+			i64 q = k0 + lane;
+			bool keep = (q < e) && (Aj[q] != j);
+			unsigned mask = __ballot_sync(0xffffffffu, keep);
+			if (keep) {
+				i64 pos = out + written + __popc(mask & ((1u << lane) - 1));
+				Uj[pos] = Aj[q];
+				Ux[pos] = zp_mul(alpha, Ax[q], F);
+			}
+			written += __popc(mask);
+		}
+	}
+}
+
+void append_pivotal_rows(const DevCsr &A, const int *d_rows, int npiv, const int *d_pinv, DevCsr &U, DevBuf<int> &Uqinv)
+{
+	if (npiv == 0)
+		return;
+	cudaStream_t s = ctx().stream;
+	Zp F = make_zp(A.prime);
+	DevBuf<i64> len((size_t) npiv + 1), off((size_t) npiv + 1);
+	len.zero(s);
+	k_urow_len<<<cdiv(npiv, 256), 256, 0, s>>>(npiv, d_rows, A.p, A.j, d_pinv, len.ptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, len.ptr, off.ptr, npiv + 1, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, len.ptr, off.ptr, npiv + 1, s);
+	LAUNCHED(2);
+	i64 extra = fetch(off.ptr + npiv);
+	/* grow U (old rows are kept) */
+	i64 unz0 = U.nnz;
+	int un0 = U.n;
+	DevBuf<i64> np((size_t) un0 + npiv + 1);
+	DevBuf<int> nj((size_t) (unz0 + extra));
+	DevBuf<i32> nx((size_t) (unz0 + extra));
+	if (un0 > 0) {
+		CUDA_CHECK(cudaMemcpyAsync(np.ptr, U.p.ptr, ((size_t) un0 + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(nj.ptr, U.j.ptr, (size_t) unz0 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(nx.ptr, U.x.ptr, (size_t) unz0 * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+	} else {
+		CUDA_CHECK(cudaMemsetAsync(np.ptr, 0, sizeof(i64), s));
+	}
+	k_urow_fill<<<std::min(cdiv((size_t) npiv * 32, 256), 148u * 16), 256, 0, s>>>(npiv, d_rows, A.p, A.j, A.x, d_pinv, off.ptr, unz0, un0,
+	                                                                                 np.ptr, nj.ptr, nx.ptr, Uqinv.ptr, F);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+	sync();
+	U.p = std::move(np);
+	U.j = std::move(nj);
+	U.x = std::move(nx);
+	U.n = un0 + npiv;
+	U.nnz = unz0 + extra;
+	U.m = A.m;
+	U.prime = A.prime;
+}
+
+}  // namespace sb

@@ -1,0 +1,360 @@
+/*
+ * Dependency graphs of U, their level schedule, and the batched pull-form
+ * triangular solve.  See solve.cuh for the formulation.
+ */
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include "solve.cuh"
+#include "stats.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sb {
+
+/* ------------------------------------------------------------------ small helpers */
+
+static void exclusive_scan_i64(const i64 *d_in, i64 *d_out, size_t n)
+{
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_in, d_out, n, ctx().stream);
+	tmp.ensure(bytes + 16);
+	cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, d_in, d_out, n, ctx().stream);
+	LAUNCHED(1);
+}
+
+template <typename K> static int coop_blocks(K kernel, int threads, size_t smem = 0)
+{
+	int occ = 0;
+	CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+	if (occ < 1)
+		errx(1, "[spasm-b200] cooperative kernel does not fit on an SM");
+	return occ * ctx().sm_count;
+}
+
+/* ------------------------------------------------------------------ forward dependency graph */
+
+/* one warp per row of U; pass 0 counts, pass 1 fills */
+template <int PASS>
+__global__ void k_fwd_deps(int n, const i64 *__restrict__ Up, const int *__restrict__ Uj, const i32 *__restrict__ Ux,
+                           unsigned long long *cnt_or_cursor, int *src, i32 *val)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (int i = warp; i < n; i += nwarps) {
+		i64 b = Up[i], e = Up[i + 1];
+		if (b == e)
+			continue;
+		int pc = Uj[b];
+		for (i64 k = b + 1 + lane; k < e; k += 32) {
+			int c = Uj[k];
+			if (c == pc)
+				continue;          /* a repeated pivot column carries no dependency (reference: pivots.c:435) */
+			if (PASS == 0) {
+				atomicAdd(&cnt_or_cursor[c], 1ull);
+			} else {
+				unsigned long long pos = atomicAdd(&cnt_or_cursor[c], 1ull);
+				src[pos] = pc;
+				val[pos] = Ux[k];
+			}
+		}
+	}
+}
+
+void depgraph_forward(const DevCsr &U, DepGraph &G)
+{
+	cudaStream_t s = ctx().stream;
+	G.nnodes = U.m;
+	DevBuf<i64> cnt((size_t) U.m + 1);
+	cnt.zero(s);
+	int blocks = std::max(1u, std::min(cdiv((size_t) U.n * 32, 256), 148u * 16));
+	if (U.n > 0) {
+		k_fwd_deps<0><<<blocks, 256, 0, s>>>(U.n, U.p, U.j, U.x, (unsigned long long *) cnt.ptr, nullptr, nullptr);
+		LAUNCHED(1);
+	}
+	G.ptr.alloc((size_t) U.m + 1);
+	exclusive_scan_i64(cnt.ptr, G.ptr.ptr, (size_t) U.m + 1);
+	G.ndeps = fetch(G.ptr.ptr + U.m);
+	G.src.alloc((size_t) std::max<i64>(G.ndeps, 1));
+	G.val.alloc((size_t) std::max<i64>(G.ndeps, 1));
+	if (U.n > 0 && G.ndeps > 0) {
+		CUDA_CHECK(cudaMemcpyAsync(cnt.ptr, G.ptr.ptr, ((size_t) U.m + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+		k_fwd_deps<1><<<blocks, 256, 0, s>>>(U.n, U.p, U.j, U.x, (unsigned long long *) cnt.ptr, G.src, G.val);
+		LAUNCHED(1);
+	}
+	KERNEL_CHECK();
+	sync();
+}
+
+/* ------------------------------------------------------------------ transposed dependency graph */
+
+template <int PASS>
+__global__ void k_tr_deps(int n, const i64 *__restrict__ Up, const int *__restrict__ Uj, const i32 *__restrict__ Ux,
+                          const int *__restrict__ qinv, i64 *cnt, const i64 *__restrict__ ptr, int *src, i32 *val)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (int i = warp; i < n; i += nwarps) {
+		i64 b = Up[i], e = Up[i + 1];
+		if (b == e)
+			continue;
+		int pc = Uj[b];
+		/* entries of row i on pivotal columns other than its own pivot; the warp compacts them in order */
+		i64 base = (PASS == 1) ? ptr[i] : 0;
+		int total = 0;
+		for (i64 k0 = b + 1; k0 < e; k0 += 32) {
+			i64 k = k0 + lane;
+			int c = (k < e) ? Uj[k] : -1;
+			int owner = (c >= 0 && c != pc) ? qinv[c] : -1;
+			unsigned mask = __ballot_sync(0xffffffffu, owner >= 0);
+			if (PASS == 1 && owner >= 0) {
+				int off = __popc(mask & ((1u << lane) - 1));
+				src[base + total + off] = owner;
+				val[base + total + off] = Ux[k];
+			}
+			total += __popc(mask);
+		}
+		if (PASS == 0 && lane == 0)
+			cnt[i] = total;
+	}
+}
+
+void depgraph_transposed(const DevCsr &U, const int *d_qinv, DepGraph &G)
+{
+	cudaStream_t s = ctx().stream;
+	G.nnodes = U.n;
+	DevBuf<i64> cnt((size_t) U.n + 1);
+	cnt.zero(s);
+	int blocks = std::max(1u, std::min(cdiv((size_t) U.n * 32, 256), 148u * 16));
+	if (U.n > 0) {
+		k_tr_deps<0><<<blocks, 256, 0, s>>>(U.n, U.p, U.j, U.x, d_qinv, cnt.ptr, nullptr, nullptr, nullptr);
+		LAUNCHED(1);
+	}
+	G.ptr.alloc((size_t) U.n + 1);
+	exclusive_scan_i64(cnt.ptr, G.ptr.ptr, (size_t) U.n + 1);
+	G.ndeps = fetch(G.ptr.ptr + U.n);
+	G.src.alloc((size_t) std::max<i64>(G.ndeps, 1));
+	G.val.alloc((size_t) std::max<i64>(G.ndeps, 1));
+	if (U.n > 0 && G.ndeps > 0) {
+		k_tr_deps<1><<<blocks, 256, 0, s>>>(U.n, U.p, U.j, U.x, d_qinv, nullptr, G.ptr, G.src, G.val);
+		LAUNCHED(1);
+	}
+	KERNEL_CHECK();
+	sync();
+}
+
+/* ------------------------------------------------------------------ level schedule (Kahn) */
+
+__global__ void k_rev_count(int nnodes, const i64 *__restrict__ ptr, const int *__restrict__ src, unsigned long long *rcnt, int *indeg)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nnodes)
+		return;
+	i64 b = ptr[c], e = ptr[c + 1];
+	indeg[c] = (int) (e - b);
+	for (i64 k = b; k < e; k++)
+		atomicAdd(&rcnt[src[k]], 1ull);
+}
+
+__global__ void k_rev_fill(int nnodes, const i64 *__restrict__ ptr, const int *__restrict__ src, unsigned long long *cursor, int *rdst)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nnodes)
+		return;
+	for (i64 k = ptr[c]; k < ptr[c + 1]; k++)
+		rdst[atomicAdd(&cursor[src[k]], 1ull)] = c;
+}
+
+__global__ void k_kahn_seed(int nnodes, const int *__restrict__ indeg, int *order, int *level, int *tail)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nnodes)
+		return;
+	if (indeg[c] == 0) {
+		order[atomicAdd(tail, 1)] = c;
+		level[c] = 0;
+	} else {
+		level[c] = -1;
+	}
+}
+
+/* persistent cooperative kernel: one frontier (= one level) per iteration */
+__global__ void k_kahn(const i64 *__restrict__ rptr, const int *__restrict__ rdst, int *indeg, int *order, int *level,
+                       int *tail, int *level_ptr, int *nlevels_out)
+{
+	cg::grid_group grid = cg::this_grid();
+	int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	int begin = 0, end = *tail, L = 0;
+	grid.sync();
+	while (begin < end) {
+		if (gtid == 0)
+			level_ptr[L] = begin;
+		for (int idx = begin + gtid; idx < end; idx += gsize) {
+			int s = order[idx];
+			for (i64 k = rptr[s]; k < rptr[s + 1]; k++) {
+				int c = rdst[k];
+				if (atomicSub(&indeg[c], 1) == 1) {
+					order[atomicAdd(tail, 1)] = c;
+					level[c] = L + 1;
+				}
+			}
+		}
+		grid.sync();
+		int newend = *((volatile int *) tail);
+		grid.sync();
+		begin = end;
+		end = newend;
+		L++;
+	}
+	if (gtid == 0) {
+		level_ptr[L] = begin;
+		*nlevels_out = L;
+	}
+}
+
+__global__ void k_make_keys(int n, const int *__restrict__ order, const int *__restrict__ level, unsigned long long *keys)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) {
+		int c = order[t];
+		keys[t] = ((unsigned long long) (unsigned) level[c] << 32) | (unsigned) c;
+	}
+}
+
+__global__ void k_keys_to_order(int n, const unsigned long long *__restrict__ keys, int *order)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n)
+		order[t] = (int) (keys[t] & 0xffffffffull);
+}
+
+void depgraph_schedule(DepGraph &G)
+{
+	cudaStream_t s = ctx().stream;
+	int n = G.nnodes;
+	G.level.alloc((size_t) n + 1);
+	G.order.alloc((size_t) n + 1);
+	G.level_ptr.alloc((size_t) n + 2);
+	G.level_ptr_h.assign(1, 0);
+	G.nlevels = 0;
+	if (n == 0)
+		return;
+	DevBuf<i64> rcnt((size_t) n + 1), rptr((size_t) n + 1);
+	DevBuf<int> indeg((size_t) n), rdst((size_t) std::max<i64>(G.ndeps, 1)), counters(2);
+	rcnt.zero(s);
+	counters.zero(s);
+	k_rev_count<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, (unsigned long long *) rcnt.ptr, indeg);
+	exclusive_scan_i64(rcnt.ptr, rptr.ptr, (size_t) n + 1);
+	CUDA_CHECK(cudaMemcpyAsync(rcnt.ptr, rptr.ptr, ((size_t) n + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+	k_rev_fill<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, (unsigned long long *) rcnt.ptr, rdst);
+	k_kahn_seed<<<cdiv(n, 256), 256, 0, s>>>(n, indeg, G.order, G.level, counters.ptr);
+	LAUNCHED(3);
+	KERNEL_CHECK();
+
+	int threads = 256;
+	int blocks = coop_blocks(k_kahn, threads);
+	const i64 *a_rptr = rptr.ptr;
+	const int *a_rdst = rdst.ptr;
+	int *a_indeg = indeg.ptr, *a_order = G.order.ptr, *a_level = G.level.ptr, *a_tail = counters.ptr;
+	int *a_lp = G.level_ptr.ptr, *a_nl = counters.ptr + 1;
+	void *args[] = {&a_rptr, &a_rdst, &a_indeg, &a_order, &a_level, &a_tail, &a_lp, &a_nl};
+	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_kahn, dim3(blocks), dim3(threads), args, 0, s));
+	LAUNCHED(1);
+	int h[2];
+	CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+	sync();
+	if (h[0] != n)
+		errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d nodes scheduled): invalid U / qinv", h[0], n);
+	G.nlevels = h[1];
+	G.level_ptr_h.resize((size_t) G.nlevels + 1);
+	CUDA_CHECK(cudaMemcpyAsync(G.level_ptr_h.data(), G.level_ptr.ptr, ((size_t) G.nlevels + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+
+	/* deterministic order inside each level: sort by (level, node) */
+	DevBuf<unsigned long long> keys((size_t) n), keys2((size_t) n);
+	k_make_keys<<<cdiv(n, 256), 256, 0, s>>>(n, G.order, G.level, keys.ptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
+	k_keys_to_order<<<cdiv(n, 256), 256, 0, s>>>(n, keys2.ptr, G.order);
+	LAUNCHED(3);
+	KERNEL_CHECK();
+	sync();
+	G.scheduled_deps = G.ndeps;
+}
+
+/* ------------------------------------------------------------------ the solve */
+
+/*
+ * Persistent cooperative kernel.  blockDim.x = 256 threads arranged as (256/TR) column slots x TR
+ * lanes; each lane owns 4 consecutive right-hand sides (one 16-byte vector).  Levels are separated
+ * by grid barriers; inside a level every scheduled column is independent.
+ */
+__global__ void __launch_bounds__(256)
+k_panel_solve(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+              const int *__restrict__ order, const int *__restrict__ level_ptr, int nlevels,
+              int4 *X, int ld4, int R4, int TR, Zp F)
+{
+	cg::grid_group grid = cg::this_grid();
+	const int tx = threadIdx.x % TR, ty = threadIdx.x / TR, CPB = blockDim.x / TR;
+	for (int L = 1; L < nlevels; L++) {
+		const int begin = level_ptr[L], ncols = level_ptr[L + 1] - begin;
+		for (int g = blockIdx.x * CPB + ty; g < ncols; g += gridDim.x * CPB) {
+			const int c = order[begin + g];
+			const i64 e0 = ptr[c], e1 = ptr[c + 1];
+			int4 *Xc = X + (size_t) c * ld4;
+			for (int r = tx; r < R4; r += TR) {
+				int4 b = Xc[r];
+				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+				int pending = 0;
+				for (i64 e = e0; e < e1; e++) {
+					const i64 v = val[e];
+					const int4 xs = X[(size_t) src[e] * ld4 + r];
+					a0 -= v * xs.x;
+					a1 -= v * xs.y;
+					a2 -= v * xs.z;
+					a3 -= v * xs.w;
+					if (++pending == F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pending = 0;
+					}
+				}
+				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
+				Xc[r] = b;
+			}
+		}
+		grid.sync();
+	}
+}
+
+void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
+{
+	if (G.nlevels <= 1 || R <= 0)
+		return;
+	if (ld % 4 != 0)
+		errx(1, "[spasm-b200] internal: panel leading dimension must be a multiple of 4");
+	int R4 = (R + 3) / 4, ld4 = ld / 4;
+	int TR = 8;
+	while (TR < R4 && TR < 256)
+		TR *= 2;
+	int blocks = coop_blocks(k_panel_solve, 256);
+	const i64 *a_ptr = G.ptr.ptr;
+	const int *a_src = G.src.ptr;
+	const i32 *a_val = G.val.ptr;
+	const int *a_order = G.order.ptr, *a_lp = G.level_ptr.ptr;
+	int nlevels = G.nlevels;
+	int4 *a_X = (int4 *) X;
+	Zp Fc = F;
+	void *args[] = {&a_ptr, &a_src, &a_val, &a_order, &a_lp, &nlevels, &a_X, &ld4, &R4, &TR, &Fc};
+	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_panel_solve, dim3(blocks), dim3(256), args, 0, ctx().stream));
+	LAUNCHED(1);
+	Stats &st = stats();
+	st.pub.solve_batches += 1;
+	st.pub.solve_rows += R;
+	/* what this formulation must move: one panel vector read per dependency, one read+write per scheduled column */
+	i64 scheduled = (i64) G.nnodes - (G.level_ptr_h.size() > 1 ? G.level_ptr_h[1] : 0);
+	st.pub.solve_traffic_model += ((double) G.ndeps + 2.0 * scheduled) * 4.0 * R;
+}
+
+}  // namespace sb
