@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the echelonization hot path (BASELINE.json: echelonize/rank time on the config-2 shape).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's own CPU path (oracle/_ref)
+
+One "step" = one spasm_echelonize of the workload (what tools/rank times, reference: tools/rank.c:100-103).
+The JSON line carries:
+  value / ms_per_step : CUDA-event time of a step with the matrix already resident in HBM (max over ranks)
+  e2e                 : the same step through the reference-facing C ABI (spasm_echelonize on host buffers:
+                        host->device copy of A, device->host copy of the echelon form U inside the timed region)
+  roofline            : the dominant kernel of the step, timed live with CUDA events inside the library
+  cpu_baseline        : oracle/_ref (the reference's C sources) on the host cores, rank 0, N=1
+Nothing here reads /root/reference; oracle/ is used only as the CPU baseline / reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "echelonize/rank time (s)"
+
+
+def peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def make_workload(name: str, scale: float):
+    from spasm_b200 import synthetic
+    if name == "config2":
+        t = synthetic.config2(scale).transposed()      # tools/rank.c:84-88 transposes when n < m
+        opts = {}
+    elif name == "config1":
+        t, opts = synthetic.config1(scale), {}
+    elif name == "config3":
+        t, opts = synthetic.config3(scale), {"sparsity_threshold": 0.01}
+    elif name == "config4":
+        t, opts = synthetic.config4(scale), {}
+    elif name == "config5":
+        t, opts = synthetic.config5(scale), {}
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return t, opts
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:6]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self) -> dict:
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args) -> None:
+    """The reference's own CPU implementation (oracle/_ref/libspasm_ref.so = /root/reference/src compiled in place,
+    dense stage restated -- not FFLAS-FFPACK), all host threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import oracle
+    from spasm_b200 import host
+    t, opts = make_workload(args.workload, args.scale)
+    R = oracle.ref()
+    kind = "reference"
+    if R is None:
+        kind = "port"
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)                      # the reference prints \r progress bars on stderr
+    try:
+        times = []
+        rank_found = None
+        if R is not None:
+            A = host.compress(R, t)
+            for step in range(args.warmup + args.steps):
+                oracle.reset_rand()
+                t0 = time.perf_counter()
+                f = host.echelonize(R, A, host.default_opts(R, **opts))
+                dt = time.perf_counter() - t0
+                rank_found = f.rank
+                if step >= args.warmup:
+                    times.append(dt)
+        else:
+            A = oracle.compress(t)
+            cores = 1
+            for step in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                e = oracle.echelonize(A, oracle.default_opts(**opts))
+                dt = time.perf_counter() - t0
+                rank_found = e.rank
+                if step >= args.warmup:
+                    times.append(dt)
+    finally:
+        os.dup2(saved, 2)
+    v = sum(times) / len(times)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 mod p (balanced)", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (scale {args.scale}): {t.n}x{t.m}, {t.nz} entries, p={t.prime}", "rank": rank_found},
+            "cpu_baseline": {"value": v, "unit": "s", "cores": cores, "kind": kind,
+                             "sample": "the full workload, every step (dense stage: restated, not FFLAS-FFPACK)"},
+            "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, t, opts) -> dict:
+    """Bounded CPU sample on the host cores: one full run of the workload through oracle/_ref."""
+    cores = os.cpu_count() or 1
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--workload", args.workload, "--scale", str(args.scale)]
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), RANK="0", WORLD_SIZE="1")
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env).stdout.strip().splitlines()
+        d = json.loads(out[-1])
+        return d["cpu_baseline"]
+    except Exception as exc:   # the baseline is reported, never required
+        return {"value": None, "unit": "s", "cores": cores, "kind": "reference", "sample": f"failed: {exc}"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("SPASM_B200_DEVICE", str(local_rank))
+
+    import torch
+    import spasm_b200
+    from spasm_b200 import host
+    import oracle     # only for srand(1): glibc rand() is part of the reference's result
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    L = spasm_b200.lib()          # raises if the CUDA library was not built: no fallback
+    L.spasm_b200_set_verbose(0)
+    t, opts = make_workload(args.workload, args.scale)
+    A = host.compress(L, t)
+    o = host.default_opts(L, **opts)
+    handle = L.spasm_b200_upload_csr(A.ptr)
+    ms = C.c_double()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps
+    for _ in range(max(args.warmup, 3)):
+        oracle.reset_rand()
+        L.spasm_b200_echelonize_resident(handle, C.byref(o), C.byref(ms))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms, agg = [], None
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        L.spasm_b200_flush_l2()              # cold L2 between timed iterations (the workload, ~10 MB, would fit in L2)
+        oracle.reset_rand()
+        L.spasm_b200_reset_stats()
+        rk = L.spasm_b200_echelonize_resident(handle, C.byref(o), C.byref(ms))
+        step_ms.append(ms.value)
+        s = spasm_b200.Stats()
+        L.spasm_b200_get_stats(C.byref(s))
+        if agg is None:
+            agg = {k: 0.0 for k in ("ms_pivots", "ms_pivots_greedy", "ms_solve", "ms_dense", "ms_dense_gemm", "ms_k_greedy",
+                                    "ms_k_panel_solve", "kernel_launches", "greedy_edges", "solve_traffic_model", "gemm_fieldops",
+                                    "solve_rows")}
+        for k in agg:
+            agg[k] += float(getattr(s, k))
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = sum(step_ms)
+
+    # ---- end-to-end steps through the reference-facing C ABI (host buffers in, host echelon form out)
+    e2e_times, h2d, d2h = [], 0, 0
+    oracle.reset_rand()
+    host.echelonize(L, A, o)                 # warm-up
+    barrier()
+    for _ in range(args.steps):
+        L.spasm_b200_flush_l2()
+        oracle.reset_rand()
+        L.spasm_b200_reset_stats()
+        t0 = time.perf_counter()
+        f = host.echelonize(L, A, o)
+        e2e_times.append(time.perf_counter() - t0)
+        s = spasm_b200.Stats()
+        L.spasm_b200_get_stats(C.byref(s))
+        h2d, d2h = int(s.h2d_bytes), int(s.d2h_bytes)
+        del f
+    barrier()
+    e2e_total = sum(e2e_times)
+
+    if dist is not None:
+        v = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(v[0]), float(v[1])
+
+    if rank == 0:
+        K = args.steps
+        ms_per_step = total_ms / K
+        # with N > 1 every rank echelonizes its own copy of the workload (replicas): N results per step time
+        value = ms_per_step / 1e3 / world
+        pk = peaks()
+        per = {k: v / K for k, v in agg.items()}
+        kernels = {"greedy_pivot_search": per["ms_k_greedy"], "panel_solve": per["ms_k_panel_solve"], "dense_echelon": per["ms_dense"]}
+        dominant = max(kernels, key=kernels.get)
+        if dominant == "greedy_pivot_search":
+            bytes_alg = 4.0 * per["greedy_edges"]        # 4 B per pivot-row entry traversed (device-counted)
+            note = "4 B x pivot-row entries traversed by the BFS (counted on the device)"
+        elif dominant == "panel_solve":
+            bytes_alg = per["solve_traffic_model"]
+            note = "4 B x R x (dependencies + 2 x scheduled columns): panel vectors the pull-form solve must move"
+        else:
+            bytes_alg = 0.0
+            note = "dense echelon (CUDA-core panels + trailing updates): see dense_modp_tops"
+        dur_s = kernels[dominant] / 1e3
+        achieved = bytes_alg / dur_s / 1e9 if dur_s > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 mod p (balanced)", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (scale {args.scale}): {t.n}x{t.m}, {t.nz} entries, p={t.prime}",
+                       "rank": int(rk), "l2": "flushed between timed steps (512 MB write)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} replicas (row sharding not enabled in this round)"},
+            "e2e": {"value": e2e_total / K / world, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(round(per["kernel_launches"])) * K,
+            "clocks": sampler.summary(),
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "bytes_per_launch": bytes_alg,
+                         "ms_per_launch": kernels[dominant], "note": note},
+            "phases_ms": {k: round(per[k], 3) for k in ("ms_pivots", "ms_pivots_greedy", "ms_k_greedy", "ms_solve", "ms_k_panel_solve",
+                                                        "ms_dense", "ms_dense_gemm")},
+            "schur_rows_per_s": per["solve_rows"] / (per["ms_solve"] / 1e3) if per["ms_solve"] > 0 else None,
+            "dense_modp_tops": per["gemm_fieldops"] / (per["ms_dense"] / 1e3) / 1e12 if per["ms_dense"] > 0 else None,
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, t, opts)
+        print(json.dumps(line), flush=True)
+    L.spasm_b200_free_csr(handle)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

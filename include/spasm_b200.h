@@ -9,6 +9,7 @@
 #ifndef _SPASM_B200_H
 #define _SPASM_B200_H
 #include <stdint.h>
+#include "spasm.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -23,7 +24,10 @@ struct spasm_b200_stats {
 	double ms_solve;              /* batched triangular solves (all callers) */
 	double ms_dense;              /* dense echelon + dense updates */
 	double ms_dense_gemm;         /*   of which the trailing-update / block-update GEMMs */
-	double ms_total_echelonize;   /* wall clock of the last spasm_echelonize call */
+	double ms_total_echelonize;   /* host wall clock of the last echelonize call */
+	double ms_device_echelonize;  /* the same call bracketed by CUDA events on the library's stream */
+	double ms_k_greedy;           /* the greedy search kernel alone */
+	double ms_k_panel_solve;      /* the panel-solve kernel launches alone */
 	/* algorithmic work */
 	double solve_bytes;           /* sum over solved rows of 8*nnz(B[k]) + 8*sum nnz(U rows reached) + output bytes */
 	int64_t solve_rows;
@@ -49,6 +53,14 @@ void spasm_b200_reset_stats(void);
 void spasm_b200_get_stats(struct spasm_b200_stats *out);
 const char *spasm_b200_version(void);
 void spasm_b200_set_verbose(int verbose);    /* 0 silences the stderr progress lines */
+
+/* Device-resident operation, for measuring the kernels without PCIe traffic: upload once, echelonize many times.
+ * The echelon form of the resident variant stays on the device and is discarded; the rank is returned and
+ * *ms_device receives the CUDA-event time of the call. */
+void *spasm_b200_upload_csr(const struct spasm_csr *A);
+void  spasm_b200_free_csr(void *handle);
+int   spasm_b200_echelonize_resident(void *handle, struct echelonize_opts *opts, double *ms_device);
+void  spasm_b200_flush_l2(void);             /* writes 512 MB: cold L2 for the next timed step */
 
 /* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
  * round after round; returns their number.  Pass NULL to query the count. */

@@ -26,7 +26,27 @@ EXTRA_PROTOTYPES = {
     "spasm_b200_reset_stats": (None, []),
     "spasm_b200_get_stats": (None, [C.c_void_p]),
     "spasm_b200_version": (C.c_char_p, []),
+    "spasm_b200_set_verbose": (None, [C.c_int]),
+    "spasm_b200_upload_csr": (C.c_void_p, [abi.CsrP]),
+    "spasm_b200_free_csr": (None, [C.c_void_p]),
+    "spasm_b200_echelonize_resident": (C.c_int, [C.c_void_p, abi.OptsP, C.POINTER(C.c_double)]),
+    "spasm_b200_flush_l2": (None, []),
+    "spasm_b200_last_pivot_pairs": (C.c_int, [abi.c_int_p, abi.c_int_p, abi.c_int_p]),
 }
+
+
+class Stats(C.Structure):
+    """ctypes mirror of struct spasm_b200_stats (include/spasm_b200.h)."""
+    _fields_ = [("kernel_launches", C.c_int64), ("ms_pivots", C.c_double), ("ms_pivots_greedy", C.c_double),
+                ("ms_solve", C.c_double), ("ms_dense", C.c_double), ("ms_dense_gemm", C.c_double),
+                ("ms_total_echelonize", C.c_double), ("ms_device_echelonize", C.c_double), ("ms_k_greedy", C.c_double),
+                ("ms_k_panel_solve", C.c_double), ("solve_bytes", C.c_double), ("solve_rows", C.c_int64),
+                ("solve_batches", C.c_int64), ("solve_traffic_model", C.c_double), ("gemm_fieldops", C.c_double),
+                ("gemm_int8_ops", C.c_double), ("greedy_edges", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("nrounds", C.c_int), ("found_FL", C.c_int * 64), ("found_FLcol", C.c_int * 64),
+                ("found_greedy", C.c_int * 64), ("density", C.c_double * 64), ("finish", C.c_int), ("nblocks", C.c_int),
+                ("block_Sn", C.c_int * 4096), ("block_Sm", C.c_int * 4096), ("block_rr", C.c_int * 4096),
+                ("block_w", C.c_int * 4096), ("dag_depth", C.c_int)]
 
 
 class MissingExtension(RuntimeError):
@@ -41,7 +61,7 @@ def lib() -> C.CDLL:
             raise MissingExtension(
                 f"{LIB_PATH} is missing: build it with `python -m spasm_b200.build` "
                 "(there is deliberately no CPU fallback for the CUDA path)")
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(LIB_PATH)        # RTLD_LOCAL: the reference library used by the tests exports the same names
         abi.bind(L)
         for name, (res, args) in EXTRA_PROTOTYPES.items():
             fn = getattr(L, name)

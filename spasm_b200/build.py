@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(_run, jobs))
     if jobs or not os.path.exists(LIB):
-        _run([NVCC] + ARCH + ["-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+        _run([NVCC] + ARCH + ["-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     if verbose:
         print(f"built {LIB} ({len(jobs)} objects recompiled)")
     return LIB

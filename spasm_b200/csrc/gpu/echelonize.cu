@@ -413,42 +413,9 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	return fact;
 }
 
-}  // namespace sb
-
-using namespace sb;
-
-/* ================================================================== C ABI */
-
-extern "C" {
-
-/* reference: src/spasm_echelonize.c:9-28 */
-void spasm_echelonize_init_opts(struct echelonize_opts *opts)
+/* reference: src/spasm_echelonize.c:473-617.  A lives in HBM already; the result stays in E. */
+static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts *opts)
 {
-	opts->enable_greedy_pivot_search = 1;
-	opts->enable_tall_and_skinny = 1;
-	opts->enable_dense = 1;
-	opts->enable_GPLU = 1;
-	opts->L = 0;
-	opts->complete = 0;
-	opts->min_pivot_proportion = 0.1;
-	opts->max_round = 3;
-	opts->sparsity_threshold = 0.05;
-	opts->tall_and_skinny_ratio = 5;
-	opts->dense_block_size = 1000;
-	opts->low_rank_ratio = 0.5;
-	opts->low_rank_start_weight = -1;
-}
-
-/* reference: src/spasm_echelonize.c:473-617 */
-struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts)
-{
-	struct echelonize_opts default_opts;
-	if (opts == NULL) {
-		LOG("[echelonize] using default settings\n");
-		opts = &default_opts;
-		spasm_echelonize_init_opts(opts);
-	}
-	double start = spasm_wtime();
 	Stats &st = stats();
 	st.pair_row.clear();
 	st.pair_col.clear();
@@ -456,9 +423,8 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 	st.pub.nrounds = 0;
 	st.pub.nblocks = 0;
 	st.pub.finish = 0;
-	int n = A->n, m = A->m;
-	i64 prime = spasm_get_prime(A);
-	LOG("[echelonize] Start on %d x %d matrix with %" PRId64 " nnz\n", n, m, spasm_nnz(A));
+	int n = dA0.n, m = dA0.m;
+	LOG("[echelonize] Start on %d x %d matrix with %" PRId64 " nnz\n", n, m, dA0.nnz);
 	if (opts->complete)
 		opts->L = 1;
 	if (opts->L)
@@ -466,17 +432,13 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 	if (opts->dense_block_size <= 0)
 		errx(1, "[spasm-b200] dense_block_size must be positive");
 
-	ctx();
-	Engine E;
-	E.init(m, prime);
-	DevCsr dA0;
-	dA0.upload(A);
+	E.init(m, dA0.prime);
 	DevCsr dS;                       /* current Schur complement once a round has run */
 	const DevCsr *cur = &dA0;
 
 	std::vector<int> p((size_t) std::max(n, 1));
 	std::vector<int> p_in;           /* empty = identity */
-	double density = (double) spasm_nnz(A) / n / m;
+	double density = (double) dA0.nnz / n / m;
 	int npiv = 0, status = 0, round;
 	for (round = 0; round < opts->max_round; round++) {
 		if (cur->nnz == 0) {
@@ -551,10 +513,99 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 			LOG("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
 		}
 	}
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+/* ================================================================== C ABI */
+
+extern "C" {
+
+/* reference: src/spasm_echelonize.c:9-28 */
+void spasm_echelonize_init_opts(struct echelonize_opts *opts)
+{
+	opts->enable_greedy_pivot_search = 1;
+	opts->enable_tall_and_skinny = 1;
+	opts->enable_dense = 1;
+	opts->enable_GPLU = 1;
+	opts->L = 0;
+	opts->complete = 0;
+	opts->min_pivot_proportion = 0.1;
+	opts->max_round = 3;
+	opts->sparsity_threshold = 0.05;
+	opts->tall_and_skinny_ratio = 5;
+	opts->dense_block_size = 1000;
+	opts->low_rank_ratio = 0.5;
+	opts->low_rank_start_weight = -1;
+}
+
+/* reference: src/spasm_echelonize.c:473-617 -- host matrix in, malloc'ed host echelon form out */
+struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts)
+{
+	struct echelonize_opts default_opts;
+	if (opts == NULL) {
+		LOG("[echelonize] using default settings\n");
+		opts = &default_opts;
+		spasm_echelonize_init_opts(opts);
+	}
+	double start = spasm_wtime();
+	ctx();
+	GpuTimer timer;
+	timer.start();
+	DevCsr dA0;
+	dA0.upload(A);
+	Engine E;
+	echelonize_core(E, dA0, opts);
 	struct spasm_lu *fact = assemble(E, 0);
-	st.pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
+	stats().pub.ms_device_echelonize = timer.stop_ms();
+	stats().pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
 	LOG("[echelonize] Done in %.3fs. Rank %d, %" PRId64 " nz in basis\n", spasm_wtime() - start, fact->U->n, spasm_nnz(fact->U));
 	return fact;
+}
+
+/* ---- device-resident variant (include/spasm_b200.h): the input stays in HBM between calls */
+void *spasm_b200_upload_csr(const struct spasm_csr *A)
+{
+	ctx();
+	DevCsr *d = new DevCsr();
+	d->upload(A);
+	sb::sync();
+	return d;
+}
+
+void spasm_b200_free_csr(void *handle) { delete (DevCsr *) handle; }
+
+int spasm_b200_echelonize_resident(void *handle, struct echelonize_opts *opts, double *ms_device)
+{
+	struct echelonize_opts default_opts;
+	if (opts == NULL) {
+		opts = &default_opts;
+		spasm_echelonize_init_opts(opts);
+	}
+	double start = spasm_wtime();
+	GpuTimer timer;
+	timer.start();
+	Engine E;
+	echelonize_core(E, *(DevCsr *) handle, opts);
+	double ms = timer.stop_ms();
+	stats().pub.ms_device_echelonize = ms;
+	stats().pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
+	if (ms_device)
+		*ms_device = ms;
+	return E.rank();
+}
+
+/* write a buffer larger than the 126 MB L2 so that the next timed step starts cold */
+void spasm_b200_flush_l2(void)
+{
+	static DevBuf<char> scrub;
+	size_t bytes = (size_t) 512 << 20;
+	scrub.ensure(bytes);
+	static int v = 0;
+	CUDA_CHECK(cudaMemsetAsync(scrub.ptr, ++v & 0xff, bytes, ctx().stream));
+	sb::sync();
 }
 
 }  /* extern "C" */

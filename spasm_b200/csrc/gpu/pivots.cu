@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 		const i64 rb = a.Ap[i], re = a.Ap[i + 1];
 
 		/* ---- begin the transaction: read the journal length, then scatter the row (pivots.c:198-215).
-		 * Done by one thread in entry order: with a repeated column the count `alive` follows the
-		 * reference's arithmetic (alive -= w[j]) exactly. */
+		 * `alive` counts DISTINCT candidate columns.  (On a row that repeats a column the reference counts the
+		 * repetitions too, which can make it select a reachable entry and close an alternating cycle,
+		 * pivots.c:232-238; that failure mode is deliberately not reproduced -- DESIGN.md, "quirks".) */
 		if (tid == 0) {
 			int np = ld_volatile(a.npiv);
 			__threadfence();
@@ -220,15 +221,14 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 				int j = a.Aj[k];
 				unsigned bit = 1u << (j & 31);
 				int word = j >> 5;
+				if ((vis[word] | srv[word]) & bit)
+					continue;                   /* repeated column */
 				if (ld_volatile(&a.qinv[j]) < 0) {
 					srv[word] |= bit;
 					alive += 1;
 				} else {
-					int wj = (srv[word] & bit) ? 1 : ((vis[word] & bit) ? -1 : 0);
 					queue[tail++] = j;
-					alive -= wj;
 					vis[word] |= bit;
-					srv[word] &= ~bit;
 				}
 			}
 			sh.head = 0;
@@ -313,26 +313,20 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 		if (tid == 0) {
 			if (sh.alive > 0) {
 				int j = -1;
-				for (i64 k = rb; k < re; k++) {     /* first survivor in row order; the last entry if none (quirk, see oracle) */
-					j = a.Aj[k];
-					if (srv[j >> 5] & (1u << (j & 31)))
+				for (i64 k = rb; k < re; k++) {     /* first survivor in row order (pivots.c:233-237) */
+					int c = a.Aj[k];
+					if (srv[c >> 5] & (1u << (c & 31))) {
+						j = c;
 						break;
-				}
-				int result = 1;
-				int oldrow = ld_volatile(&a.qinv[j]);
-				if (oldrow != -1) {                  /* only reachable through rows with a repeated column */
-					a.pinv[oldrow] = -1;
-					result = 0;
+					}
 				}
 				a.pinv[i] = j;
 				*((volatile int *) &a.qinv[j]) = i;
 				int np = ld_volatile(a.npiv);
 				a.journal[np] = j;
 				__threadfence();
-				if (result) {
-					*((volatile int *) a.npiv) = np + 1;
-					atomicAdd(a.found, 1);
-				}
+				*((volatile int *) a.npiv) = np + 1;
+				atomicAdd(a.found, 1);
 			}
 			__threadfence();
 			*((volatile int *) &a.status[i]) = 1;
@@ -356,43 +350,6 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 	}
 	if (my_edges)
 		atomicAdd(a.edges, my_edges);
-}
-
-/* rows holding the same column twice (possible only through the compress quirk) */
-__global__ void k_row_keys(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, unsigned long long *keys)
-{
-	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (int i = warp; i < n; i += nwarps)
-		for (i64 k = Ap[i] + lane; k < Ap[i + 1]; k += 32)
-			keys[k] = ((unsigned long long) (unsigned) i << 32) | (unsigned) Aj[k];
-}
-
-__global__ void k_adjacent_equal(i64 nnz, const unsigned long long *__restrict__ keys, int *flag)
-{
-	i64 k = (i64) blockIdx.x * blockDim.x + threadIdx.x;
-	if (k + 1 < nnz && keys[k] == keys[k + 1])
-		*flag = 1;
-}
-
-static bool has_repeated_columns(const DevCsr &A)
-{
-	if (A.nnz < 2)
-		return false;
-	cudaStream_t s = ctx().stream;
-	DevBuf<unsigned long long> keys((size_t) A.nnz), sorted((size_t) A.nnz);
-	DevBuf<int> flag(1);
-	flag.zero(s);
-	k_row_keys<<<std::min(cdiv((size_t) A.n * 32, 256), 148u * 8), 256, 0, s>>>(A.n, A.p, A.j, keys.ptr);
-	static DevBuf<char> tmp;
-	size_t bytes = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.ptr, sorted.ptr, (int) A.nnz, 0, 64, s);
-	tmp.ensure(bytes + 16);
-	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, sorted.ptr, (int) A.nnz, 0, 64, s);
-	k_adjacent_equal<<<cdiv((size_t) A.nnz, 256), 256, 0, s>>>(A.nnz, sorted.ptr, flag.ptr);
-	LAUNCHED(3);
-	KERNEL_CHECK();
-	return fetch(flag.ptr) != 0;
 }
 
 /* ============================================================ driver */
@@ -448,7 +405,6 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 	if (greedy) {
 		GpuTimer timer;
 		timer.start();
-		bool sequential = has_repeated_columns(A);
 		GreedyArgs a;
 		a.n = n;
 		a.m = m;
@@ -466,7 +422,7 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy, 256, smem));
 		if (occ < 1)
 			errx(1, "[spasm-b200] greedy pivot search kernel does not fit");
-		int blocks = sequential ? 1 : std::min(occ, 8) * ctx().sm_count;
+		int blocks = std::min(occ, 8) * ctx().sm_count;
 		blocks = std::min(blocks, std::max(1, n));
 		/* longest row bounds the extra queue slots used by the initial scatter */
 		a.queue_cap = m + 64;
@@ -495,9 +451,12 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		a.bitmaps = bitmaps.ptr;
 		a.queues = queues.ptr;
 		a.edges = edges.ptr;
+		GpuTimer tk;
+		tk.start();
 		k_greedy<<<blocks, 256, smem, s>>>(a);
 		LAUNCHED(1);
 		KERNEL_CHECK();
+		stats().pub.ms_k_greedy += tk.stop_ms();
 		out.greedy = fetch(counters.ptr + 4);
 		stats().pub.greedy_edges += (i64) fetch(edges.ptr);
 		stats().pub.ms_pivots_greedy += timer.stop_ms();

@@ -347,8 +347,11 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 	int4 *a_X = (int4 *) X;
 	Zp Fc = F;
 	void *args[] = {&a_ptr, &a_src, &a_val, &a_order, &a_lp, &nlevels, &a_X, &ld4, &R4, &TR, &Fc};
+	GpuTimer tk;
+	tk.start();
 	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_panel_solve, dim3(blocks), dim3(256), args, 0, ctx().stream));
 	LAUNCHED(1);
+	stats().pub.ms_k_panel_solve += tk.stop_ms();
 	Stats &st = stats();
 	st.pub.solve_batches += 1;
 	st.pub.solve_rows += R;

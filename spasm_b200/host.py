@@ -198,7 +198,7 @@ def ffpack_rref(lib, prime: int, M: np.ndarray):
     n, m = M.shape
     dt = lib.spasm_datatype_choose(prime)
     npdt = {abi.SPASM_DOUBLE: np.float64, abi.SPASM_FLOAT: np.float32, abi.SPASM_I64: np.int64}[dt]
-    A = np.ascontiguousarray(M, npdt)
+    A = np.array(M, dtype=npdt, order="C", copy=True)       # the call works in place
     qinv = (C.c_size_t * max(m, 1))()
     r = lib.spasm_ffpack_rref(prime, n, m, A.ctypes.data_as(C.c_void_p), m, dt, qinv)
     return r, np.array(list(qinv)[:m], np.int64), A.astype(np.int64)

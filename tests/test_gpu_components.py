@@ -1,0 +1,136 @@
+"""The individual entry points of the hot path against the oracle (reference: tests/schur.c, tests/schur_dense.c,
+tests/dense_rref_ffpack.c), through the C ABI on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import util
+from spasm_b200 import abi, host, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs():
+    return [synthetic.config1(0.05), synthetic.config2(0.02).transposed(), synthetic.config4(0.01), synthetic.config5(0.04),
+            synthetic.config3(0.01)]
+
+
+def _oracle_pivots(t):
+    A = oracle.compress(t)
+    pinv = np.zeros(max(t.n, 1), np.int32)
+    qinv = np.zeros(max(t.m, 1), np.int32)
+    counts = (C.c_int * 3)()
+    edges = C.c_int64()
+    oracle.lib().oracle_pivots_find(A.ptr, 1, oracle._ip(pinv), oracle._ip(qinv), counts, C.byref(edges))
+    return A, pinv[:t.n], qinv[:t.m], list(counts)
+
+
+@pytest.mark.parametrize("t", _inputs(), ids=lambda t: t.name)
+def test_pivots_extract_structural(product, t):
+    """same (row, column) pairs as the sequential reference; U rows are the pivotal rows scaled to a unit pivot"""
+    Ao, pinv, qinv, counts = _oracle_pivots(t)
+    A = host.compress(product, t)
+    npiv, p, fact = host.pivots_extract_structural(product, A)
+    assert npiv == sum(counts)
+    rows, cols = host.fact_pairs(fact, p, npiv)
+    assert set(zip(rows.tolist(), cols.tolist())) == {(int(qinv[j]), j) for j in range(t.m) if qinv[j] >= 0}
+    assert sorted(p.tolist()) == list(range(t.n))
+    assert (np.diff(p[npiv:]) > 0).all()                       # non-pivotal rows by increasing index (pivots.c:353-357)
+    U = abi.csr_to_numpy(fact.U)
+    a = A.numpy()
+    for k in range(0, npiv, max(1, npiv // 50)):
+        i, j = int(rows[k]), int(cols[k])
+        ra = dict(zip(a["j"][a["p"][i]:a["p"][i + 1]].tolist(), a["x"][a["p"][i]:a["p"][i + 1]].tolist()))
+        ru = dict(zip(U["j"][U["p"][k]:U["p"][k + 1]].tolist(), U["x"][U["p"][k]:U["p"][k + 1]].tolist()))
+        assert U["j"][U["p"][k]] == j and ru[j] == 1
+        inv = pow(ra[j] % t.prime, -1, t.prime)
+        assert all((ru[c] - ra[c] * inv) % t.prime == 0 for c in ra)
+    # U is triangular in its row order: an entry on a pivotal column belongs to a later row
+    Uq = np.ctypeslib.as_array(fact.qinv, shape=(t.m,))
+    owner = Uq[U["j"]]
+    row_of = np.repeat(np.arange(U["n"]), np.diff(U["p"]))
+    first = np.zeros(len(U["j"]), bool)
+    first[U["p"][:-1]] = True
+    assert ((owner < 0) | first | (owner > row_of)).all()
+    product.spasm_csr_free(fact.U)
+
+
+@pytest.mark.parametrize("t", _inputs(), ids=lambda t: t.name)
+def test_schur_dense_and_density_and_sparse(product, t):
+    Ao, pinv, qinv, counts = _oracle_pivots(t)
+    A = host.compress(product, t)
+    npiv, p, fact = host.pivots_extract_structural(product, A)
+    U = abi.csr_to_numpy(fact.U)
+    Uq = np.ctypeslib.as_array(fact.qinv, shape=(t.m,)).copy()
+    Uo = oracle.from_numpy(U)
+    rows = np.ascontiguousarray(p[npiv:npiv + 200], np.int32)
+    n = len(rows)
+    Sm = t.m - npiv
+    # dense block (reference: tests/schur_dense.c)
+    S, q = host.schur_dense(product, A, rows, n, fact)
+    So = np.zeros((max(n, 1), max(Sm, 1)), np.int32)
+    qo = np.zeros(max(t.m, 1), np.int32)
+    oracle.lib().oracle_schur_dense(Ao.ptr, oracle._ip(rows), n, Uo.ptr, oracle._ip(Uq), So.ctypes.data_as(C.POINTER(C.c_int32)), oracle._ip(qo))
+    assert np.array_equal(q, qo[:Sm])
+    assert np.array_equal(S, So[:n, :Sm].astype(np.int64))
+    # density estimate: same rand() draws, same value (reference: src/spasm_schur.c:11-44)
+    rest = np.ascontiguousarray(p[npiv:], np.int32)
+    if len(rest):
+        oracle.reset_rand()
+        d_gpu = product.spasm_schur_estimate_density(A.ptr, abi.as_int_p(rest), len(rest), fact.U, fact.qinv, 100)
+        oracle.reset_rand()
+        d_cpu = oracle.lib().oracle_schur_estimate_density(Ao.ptr, oracle._ip(rest), len(rest), Uo.ptr, oracle._ip(Uq), 100)
+        assert d_gpu == d_cpu
+    # sparse Schur complement (reference: tests/schur.c): same rows, same entries; order inside a row is canonicalised
+    p_out = np.zeros(max(n, 1), np.int32)
+    Sg = host.CsrHandle(product, product.spasm_schur(A.ptr, abi.as_int_p(rows), n, C.byref(fact), 1.0, None, None, abi.as_int_p(p_out))).numpy()
+    Sc = oracle.Matrix(oracle.lib().oracle_schur(Ao.ptr, oracle._ip(rows), n, Uo.ptr, oracle._ip(Uq), 1.0)).numpy()
+    assert np.array_equal(Sg["p"], Sc["p"]) and np.array_equal(p_out[:n], rows)
+    for r in range(n):
+        g = sorted(zip(Sg["j"][Sg["p"][r]:Sg["p"][r + 1]].tolist(), Sg["x"][Sg["p"][r]:Sg["p"][r + 1]].tolist()))
+        c = sorted(zip(Sc["j"][Sc["p"][r]:Sc["p"][r + 1]].tolist(), Sc["x"][Sc["p"][r]:Sc["p"][r + 1]].tolist()))
+        assert g == c
+    assert (Uq[Sg["j"]] < 0).all()                             # no entry of S under a pivot (tests/schur.c:60-70)
+    # randomized block: same rand() + PRNG stream -> identical block (reference: src/spasm_schur.c:346-413)
+    for N, w in ((17, 5), (4, 0)):
+        dt = product.spasm_datatype_choose(t.prime)
+        npdt = {abi.SPASM_DOUBLE: np.float64, abi.SPASM_FLOAT: np.float32, abi.SPASM_I64: np.int64}[dt]
+        Sr = np.zeros((N, max(Sm, 1)), npdt)
+        q2 = np.zeros(max(t.m, 1), np.int32)
+        oracle.reset_rand()
+        product.spasm_schur_dense_randomized(A.ptr, abi.as_int_p(rest), len(rest), fact.U, fact.qinv, Sr.ctypes.data_as(C.c_void_p), dt,
+                                             abi.as_int_p(q2), N, w)
+        Sro = np.zeros((N, max(Sm, 1)), np.int32)
+        oracle.reset_rand()
+        oracle.lib().oracle_schur_dense_randomized(Ao.ptr, oracle._ip(rest), len(rest), Uo.ptr, oracle._ip(Uq),
+                                                   Sro.ctypes.data_as(C.POINTER(C.c_int32)), oracle._ip(qo), N, w)
+        assert np.array_equal(Sr[:, :Sm].astype(np.int64), Sro[:, :Sm].astype(np.int64))
+    product.spasm_csr_free(fact.U)
+
+
+@pytest.mark.parametrize("prime", [3, 257, 42013, 189812507, 2147483629, 4294967291])
+@pytest.mark.parametrize("shape", [(1, 1), (5, 9), (40, 40), (130, 70), (64, 300), (257, 129)])
+def test_dense_rref_matches_oracle(product, prime, shape):
+    """spasm_ffpack_rref boundary (reference: src/spasm_ffpack.cpp:78-86, tests/dense_rref_ffpack.c): rank, column rank
+    profile and the packed RREF values, against the restated FFPACK of the oracle; rank-deficient inputs included."""
+    n, m = shape
+    rng = np.random.default_rng(prime % 1000 + n * m)
+    half = prime // 2
+    r = max(1, min(n, m) * 2 // 3)
+    Lf = rng.integers(-half, half + 1, size=(n, r)).astype(object)
+    Rf = rng.integers(-half, half + 1, size=(r, m)).astype(object)
+    Rf[:, : m // 4] = 0                                        # leading zero columns: pivots do not start at column 0
+    M = (Lf.dot(Rf)) % prime
+    M = np.where(M > half, M - prime, M).astype(np.int64)
+    rank, qinv, packed = host.ffpack_rref(product, prime, M)
+    W = np.ascontiguousarray(M, np.int32)
+    pivcol = np.zeros(max(m, 1), np.int32)
+    ro = oracle.lib().oracle_dense_rref_i32(prime, n, m, W.ctypes.data_as(C.POINTER(C.c_int32)), oracle._ip(pivcol))
+    assert rank == ro
+    assert np.array_equal(qinv[:rank], pivcol[:rank])
+    assert sorted(qinv.tolist()) == list(range(m))
+    for i in range(rank):
+        for k in range(rank, m):
+            assert packed[i, k] == W[i, qinv[k]]

@@ -15,16 +15,7 @@ from spasm_b200 import abi, host, synthetic
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-class Stats(C.Structure):
-    _fields_ = [("kernel_launches", C.c_int64), ("ms_pivots", C.c_double), ("ms_pivots_greedy", C.c_double),
-                ("ms_solve", C.c_double), ("ms_dense", C.c_double), ("ms_dense_gemm", C.c_double),
-                ("ms_total_echelonize", C.c_double), ("solve_bytes", C.c_double), ("solve_rows", C.c_int64),
-                ("solve_batches", C.c_int64), ("solve_traffic_model", C.c_double), ("gemm_fieldops", C.c_double),
-                ("gemm_int8_ops", C.c_double), ("greedy_edges", C.c_int64), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("nrounds", C.c_int), ("found_FL", C.c_int * 64), ("found_FLcol", C.c_int * 64),
-                ("found_greedy", C.c_int * 64), ("density", C.c_double * 64), ("finish", C.c_int), ("nblocks", C.c_int),
-                ("block_Sn", C.c_int * 4096), ("block_Sm", C.c_int * 4096), ("block_rr", C.c_int * 4096),
-                ("block_w", C.c_int * 4096), ("dag_depth", C.c_int)]
+from spasm_b200 import Stats  # noqa: E402  (ctypes mirror of struct spasm_b200_stats)
 
 
 def product_stats(L) -> Stats:
@@ -144,3 +135,32 @@ def load_sms(path: str, prime: int) -> synthetic.Triplets:
     arr = np.array(rows, dtype=np.int64).reshape(-1, 3)
     return synthetic.Triplets(n, m, prime, arr[:, 0].astype(np.int32), arr[:, 1].astype(np.int32), arr[:, 2].copy(),
                               os.path.basename(path))
+
+
+# ------------------------------------------------------------------ golden vectors (tests/golden/make_golden.py)
+
+def golden_cases():
+    import json
+    with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+_fixtures = None
+
+
+def golden_input(case) -> synthetic.Triplets:
+    global _fixtures
+    if case["kind"] == "fixture":
+        if _fixtures is None:
+            _fixtures = np.load(os.path.join(GOLDEN_DIR, "fixtures.npz"))
+        b = case["name"]
+        n, m = (int(v) for v in _fixtures[f"{b}.shape"])
+        return synthetic.Triplets(n, m, case["prime"], _fixtures[f"{b}.i"], _fixtures[f"{b}.j"], _fixtures[f"{b}.x"], b)
+    if case["name"] == "config2T":
+        return synthetic.config2(case["scale"]).transposed()
+    return synthetic.CONFIGS[case["name"]](case["scale"])
+
+
+def case_id(case) -> str:
+    extra = "".join(f"-{k}={v}" for k, v in case["opts"].items())
+    return f'{case["name"]}{("@" + str(case["scale"])) if "scale" in case else ""}-p{case["prime"]}{extra}'
