@@ -62,6 +62,10 @@ void  spasm_b200_free_csr(void *handle);
 int   spasm_b200_echelonize_resident(void *handle, struct echelonize_opts *opts, double *ms_device);
 void  spasm_b200_flush_l2(void);             /* writes 512 MB: cold L2 for the next timed step */
 
+/* first `count` outputs of the device implementation of the reference's PRNG stream (prime, seed, seq);
+ * for the known-answer test against tests/Expected/prng */
+void spasm_b200_prng_stream(int64_t prime, uint64_t seed, uint32_t seq, int count, int32_t *out_host);
+
 /* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
  * round after round; returns their number.  Pass NULL to query the count. */
 int spasm_b200_last_pivot_pairs(int *rows, int *cols, int *round_start /* size nrounds+1 */);

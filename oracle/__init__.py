@@ -64,6 +64,9 @@ def build(with_ref: bool | None = None) -> None:
         with_ref = os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
     if with_ref:
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "spasm_b200", "lib", "libspasm_b200.so")):
+            # the reference's unmodified tools linked against the product library
+            subprocess.run(["make", "-s", "-C", HERE, "b200_tools"], check=True)
 
 
 def lib() -> C.CDLL:

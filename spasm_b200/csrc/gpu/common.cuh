@@ -61,17 +61,19 @@ template <typename T> struct DevBuf {
 		return *this;
 	}
 	~DevBuf() { release(); }
+	/* stream-ordered allocation from the device's memory pool: no device-wide synchronisation on free,
+	 * freed blocks are reused by the next call (the drivers allocate many short-lived work arrays) */
 	void alloc(size_t n) {
 		release();
 		count = n;
 		if (n > 0)
-			CUDA_CHECK(cudaMalloc((void **) &ptr, n * sizeof(T)));
+			CUDA_CHECK(cudaMallocAsync((void **) &ptr, n * sizeof(T), ctx().stream));
 	}
 	/* grow (contents are NOT preserved) */
 	void ensure(size_t n) { if (n > count) alloc(n); }
 	void release() {
 		if (ptr)
-			cudaFree(ptr);
+			cudaFreeAsync(ptr, ctx().stream);
 		ptr = nullptr;
 		count = 0;
 	}

@@ -41,6 +41,11 @@ Context &ctx()
 	g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
 	g_ctx.verbose = g_verbose;
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+	/* keep freed blocks in the pool instead of returning them to the driver at every synchronisation */
+	cudaMemPool_t pool;
+	CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+	unsigned long long keep = ~0ull;
+	CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 	return g_ctx;
 }
 

@@ -204,6 +204,8 @@ void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
 	sync();
 }
 
+void prng_combo_coefficients(i64 prime, int N, int w, i32 *d_coef);     /* prng.cu */
+
 /* ------------------------------------------------------------------ finishing strategies */
 
 static void record_block(int Sn, int Sm, int rr, int w)
@@ -227,27 +229,31 @@ static void randomized_block(Engine &E, const DevCsr &A, const int *p, int n, in
 	cudaStream_t s = ctx().stream;
 	int ww = (w <= 0) ? n : w;
 	std::vector<int> rows((size_t) N * ww);
-	std::vector<i32> coef((size_t) N * ww);
-	for (int k = 0; k < N; k++) {
-		spasm_prng_ctx prng;
-		spasm_prng_seed_simple(E.prime, (u64) k, 0, &prng);
-		if (w <= 0) {
+	DevBuf<int> d_rows;
+	DevBuf<i32> d_coef((size_t) N * ww);
+	if (w <= 0) {
+		/* full combinations (completion test only): one coefficient per row, drawn on the host */
+		std::vector<i32> coef((size_t) N * ww);
+		for (int k = 0; k < N; k++) {
+			spasm_prng_ctx prng;
+			spasm_prng_seed_simple(E.prime, (u64) k, 0, &prng);
 			for (int i = 0; i < n; i++) {
 				rows[(size_t) k * ww + i] = p[i];
 				coef[(size_t) k * ww + i] = spasm_prng_ZZp(&prng);
 			}
-		} else {
-			for (int t = 0; t < w; t++) {
-				rows[(size_t) k * ww + t] = p[rand() % n];
-				coef[(size_t) k * ww + t] = (t == 0) ? 1 : spasm_prng_ZZp(&prng);
-			}
 		}
+		CUDA_CHECK(cudaMemcpyAsync(d_coef.ptr, coef.data(), coef.size() * sizeof(i32), cudaMemcpyHostToDevice, s));
+		sync();
+	} else {
+		/* the row choices are the reference's glibc rand() sequence (host, k-major); the coefficients come
+		 * from the SHA-256 streams, generated on the device (prng.cu) */
+		for (int k = 0; k < N; k++)
+			for (int t = 0; t < w; t++)
+				rows[(size_t) k * ww + t] = p[rand() % n];
+		prng_combo_coefficients(E.prime, N, w, d_coef.ptr);
 	}
-	DevBuf<int> d_rows;
-	DevBuf<i32> d_coef;
 	d_rows.upload(rows.data(), rows.size(), s);
-	d_coef.upload(coef.data(), coef.size(), s);
-	stats().pub.h2d_bytes += (i64) rows.size() * 8;
+	stats().pub.h2d_bytes += (i64) rows.size() * 4;
 	E.solve_combos(A, d_rows.ptr, d_coef.ptr, N, ww);
 	ldB = (E.Sm0 + 3) & ~3;
 	B.ensure((size_t) N * std::max(ldB, 4));

@@ -159,7 +159,7 @@ struct GreedyArgs {
 __device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
 
 struct GreedyShared {
-	int row, head, tail, alive, npiv_local, scan, replayed;
+	int row, head, tail, alive, npiv_local, scan, replayed, np_now, turn;
 };
 
 __device__ __forceinline__ void greedy_mark(int c, unsigned *vis, unsigned *srv, int *queue, GreedyShared *sh)
@@ -175,7 +175,7 @@ __device__ __forceinline__ void greedy_mark(int c, unsigned *vis, unsigned *srv,
 	queue[atomicAdd(&sh->tail, 1)] = c;
 }
 
-__global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
+__global__ void __launch_bounds__(256, 8) k_greedy(GreedyArgs a)
 {
 	extern __shared__ unsigned dyn_smem[];
 	__shared__ GreedyShared sh;
@@ -238,9 +238,15 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 		}
 		__syncthreads();
 
-		bool my_turn = false;
+		/* ---- search / replay / wait loop.
+		 * The BFS is kept closed under the pivots published so far WHILE the row waits for its turn: every poll
+		 * replays the journal entries it has not seen (pivots.c:260-274).  When the turn comes (every lower row is
+		 * resolved, so nobody else can commit) at most the last few entries remain to be replayed: the serial
+		 * section of a commit stays short.  A row whose survivors are exhausted is resolved at once, out of
+		 * order: reachability only grows with the pivot set. */
+		bool final_pass = false;
 		for (;;) {
-			/* ---- BFS along alternating paths (pivots.c:218-225), one frontier slice per iteration */
+			/* BFS along alternating paths (pivots.c:218-225), one slice of the queue per iteration */
 			for (;;) {
 				const int head = sh.head, tail = sh.tail, alive = sh.alive;
 				__syncthreads();
@@ -261,30 +267,30 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 					sh.head = head + cnt;
 				__syncthreads();
 			}
-			if (sh.alive <= 0)
-				break;                          /* no survivor: final, whatever happens later */
-			if (!my_turn) {
-				/* ---- wait until every lower row is resolved: from here on nobody else commits */
-				if (tid == 0) {
-					int k = max(sh.scan, ld_volatile(a.hint));
-					while (k < i) {
-						if (ld_volatile(&a.status[k]))
-							k++;
-						else
-							__nanosleep(100);
-					}
-					__threadfence();
-					sh.scan = k;
-				}
-				__syncthreads();
-				my_turn = true;
+			if (sh.alive <= 0 || final_pass)
+				break;                          /* no survivor: final, whatever happens later; or exact state at our turn */
+			/* poll: new pivots?  our turn? */
+			if (tid == 0) {
+				int k = max(sh.scan, ld_volatile(a.hint));
+				while (k < i && ld_volatile(&a.status[k]))
+					k++;
+				sh.scan = k;
+				__threadfence();
+				sh.np_now = ld_volatile(a.npiv);     /* read AFTER the status scan: includes every commit of the rows below k */
+				sh.turn = (k >= i);
 			}
-			/* ---- replay the pivots committed since the transaction began (pivots.c:260-274) */
-			const int np_now = ld_volatile(a.npiv);
-			const int np_old = sh.npiv_local;
 			__syncthreads();
-			if (np_now == np_old)
-				break;                          /* state is exact: commit */
+			const int np_now = sh.np_now, np_old = sh.npiv_local;
+			const bool turn = sh.turn;
+			__syncthreads();
+			if (np_now == np_old) {
+				if (turn)
+					break;                      /* closed under every pivot that can precede this row: commit */
+				__nanosleep(40);
+				continue;
+			}
+			if (turn)
+				final_pass = true;              /* nobody else can commit any more: after this replay the state is exact */
 			for (int t = np_old + tid; t < np_now; t += T) {
 				int j = ld_volatile(&a.journal[t]);
 				unsigned bit = 1u << (j & 31);
@@ -308,6 +314,7 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 				sh.npiv_local = np_now;
 			__syncthreads();
 		}
+		const bool my_turn = true;              /* (a commit only happens at the row's turn; a failure needs none) */
 
 		/* ---- commit (pivots.c:227-255) */
 		if (tid == 0) {
@@ -330,8 +337,8 @@ __global__ void __launch_bounds__(256) k_greedy(GreedyArgs a)
 			}
 			__threadfence();
 			*((volatile int *) &a.status[i]) = 1;
-			if (my_turn)
-				atomicMax(a.hint, i + 1);      /* every row up to i is resolved */
+			if (sh.alive > 0 && my_turn)
+				atomicMax(a.hint, i + 1);      /* a commit happens at the row's turn: every row up to i is resolved */
 		}
 		__syncthreads();
 
@@ -414,15 +421,19 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		a.qinv = d_qinv;
 		a.pinv = d_pinv;
 		size_t bitmap_bytes = (size_t) 2 * a.words * sizeof(unsigned);
-		a.use_smem = bitmap_bytes <= 200 * 1024;
+		/* tuning knobs (development): threads per CTA, bitmaps in shared or global memory, CTAs per SM */
+		int threads = getenv("SPASM_B200_GREEDY_THREADS") ? atoi(getenv("SPASM_B200_GREEDY_THREADS")) : 256;
+		int want_smem = getenv("SPASM_B200_GREEDY_SMEM") ? atoi(getenv("SPASM_B200_GREEDY_SMEM")) : 1;
+		int per_sm = getenv("SPASM_B200_GREEDY_PER_SM") ? atoi(getenv("SPASM_B200_GREEDY_PER_SM")) : 8;
+		a.use_smem = want_smem && bitmap_bytes <= 200 * 1024;
 		size_t smem = a.use_smem ? bitmap_bytes : 0;
 		if (smem > 0)
 			CUDA_CHECK(cudaFuncSetAttribute(k_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		int occ = 0;
-		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy, 256, smem));
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy, threads, smem));
 		if (occ < 1)
 			errx(1, "[spasm-b200] greedy pivot search kernel does not fit");
-		int blocks = std::min(occ, 8) * ctx().sm_count;
+		int blocks = std::min(occ, per_sm) * ctx().sm_count;
 		blocks = std::min(blocks, std::max(1, n));
 		/* longest row bounds the extra queue slots used by the initial scatter */
 		a.queue_cap = m + 64;
@@ -453,7 +464,7 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		a.edges = edges.ptr;
 		GpuTimer tk;
 		tk.start();
-		k_greedy<<<blocks, 256, smem, s>>>(a);
+		k_greedy<<<blocks, threads, smem, s>>>(a);
 		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_greedy += tk.stop_ms();

@@ -286,42 +286,61 @@ void depgraph_schedule(DepGraph &G)
 
 /* ------------------------------------------------------------------ the solve */
 
+/* one work item = 4 consecutive right-hand sides (one 16-byte vector) of one scheduled column */
+__device__ __forceinline__ void solve_item(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+                                           int c, int r, int4 *X, int ld4, const Zp &F)
+{
+	const i64 e0 = ptr[c], e1 = ptr[c + 1];
+	int4 *Xc = X + (size_t) c * ld4;
+	int4 b = Xc[r];
+	i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+	int pending = 0;
+	for (i64 e = e0; e < e1; e++) {
+		const i64 v = val[e];
+		const int4 xs = X[(size_t) src[e] * ld4 + r];
+		a0 -= v * xs.x;
+		a1 -= v * xs.y;
+		a2 -= v * xs.z;
+		a3 -= v * xs.w;
+		if (++pending == F.delay) {
+			a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+			pending = 0;
+		}
+	}
+	b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
+	Xc[r] = b;
+}
+
 /*
- * Persistent cooperative kernel.  blockDim.x = 256 threads arranged as (256/TR) column slots x TR
- * lanes; each lane owns 4 consecutive right-hand sides (one 16-byte vector).  Levels are separated
- * by grid barriers; inside a level every scheduled column is independent.
+ * Persistent cooperative kernel, one CTA of 1024 threads per SM.
+ * The schedule is a list of segments.  A WIDE segment is one level: its (column, vector) items are spread over
+ * the whole grid and a grid barrier follows.  A NARROW segment is a run of consecutive levels that each hold
+ * few columns (the long tail of the pivot DAG: thousands of levels of ~10 columns): CTA 0 walks the run alone,
+ * separated by block barriers only, while the other CTAs wait at the single grid barrier that ends the run.
  */
-__global__ void __launch_bounds__(256)
+struct SolveSegment { int level_begin, level_end, narrow; };
+
+__global__ void __launch_bounds__(1024, 1)
 k_panel_solve(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
-              const int *__restrict__ order, const int *__restrict__ level_ptr, int nlevels,
-              int4 *X, int ld4, int R4, int TR, Zp F)
+              const int *__restrict__ order, const int *__restrict__ level_ptr, const SolveSegment *__restrict__ segs, int nsegs,
+              int4 *X, int ld4, int R4, Zp F)
 {
 	cg::grid_group grid = cg::this_grid();
-	const int tx = threadIdx.x % TR, ty = threadIdx.x / TR, CPB = blockDim.x / TR;
-	for (int L = 1; L < nlevels; L++) {
-		const int begin = level_ptr[L], ncols = level_ptr[L + 1] - begin;
-		for (int g = blockIdx.x * CPB + ty; g < ncols; g += gridDim.x * CPB) {
-			const int c = order[begin + g];
-			const i64 e0 = ptr[c], e1 = ptr[c + 1];
-			int4 *Xc = X + (size_t) c * ld4;
-			for (int r = tx; r < R4; r += TR) {
-				int4 b = Xc[r];
-				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
-				int pending = 0;
-				for (i64 e = e0; e < e1; e++) {
-					const i64 v = val[e];
-					const int4 xs = X[(size_t) src[e] * ld4 + r];
-					a0 -= v * xs.x;
-					a1 -= v * xs.y;
-					a2 -= v * xs.z;
-					a3 -= v * xs.w;
-					if (++pending == F.delay) {
-						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
-						pending = 0;
-					}
-				}
-				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
-				Xc[r] = b;
+	const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (int sgi = 0; sgi < nsegs; sgi++) {
+		const SolveSegment sg = segs[sgi];
+		if (!sg.narrow) {
+			const int begin = level_ptr[sg.level_begin];
+			const i64 items = (i64) (level_ptr[sg.level_begin + 1] - begin) * R4;
+			for (i64 it = gtid; it < items; it += gsize)
+				solve_item(ptr, src, val, order[begin + (int) (it / R4)], (int) (it % R4), X, ld4, F);
+		} else if (blockIdx.x == 0) {
+			for (int L = sg.level_begin; L < sg.level_end; L++) {
+				const int begin = level_ptr[L];
+				const int items = (level_ptr[L + 1] - begin) * R4;
+				for (int it = threadIdx.x; it < items; it += blockDim.x)
+					solve_item(ptr, src, val, order[begin + it / R4], it % R4, X, ld4, F);
+				__syncthreads();
 			}
 		}
 		grid.sync();
@@ -335,21 +354,39 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 	if (ld % 4 != 0)
 		errx(1, "[spasm-b200] internal: panel leading dimension must be a multiple of 4");
 	int R4 = (R + 3) / 4, ld4 = ld / 4;
-	int TR = 8;
-	while (TR < R4 && TR < 256)
-		TR *= 2;
-	int blocks = coop_blocks(k_panel_solve, 256);
+	cudaStream_t s = ctx().stream;
+	/* segments: a level is narrow when one CTA covers it in at most two passes */
+	std::vector<SolveSegment> segs;
+	const int narrow_items = getenv("SPASM_B200_NARROW_ITEMS") ? atoi(getenv("SPASM_B200_NARROW_ITEMS")) : 2048;
+	for (int L = 1; L < G.nlevels;) {
+		i64 items = (i64) (G.level_ptr_h[L + 1] - G.level_ptr_h[L]) * R4;
+		if (items > narrow_items) {
+			segs.push_back({L, L + 1, 0});
+			L++;
+		} else {
+			int E = L;
+			while (E < G.nlevels && (i64) (G.level_ptr_h[E + 1] - G.level_ptr_h[E]) * R4 <= narrow_items)
+				E++;
+			segs.push_back({L, E, 1});
+			L = E;
+		}
+	}
+	DevBuf<SolveSegment> d_segs;
+	d_segs.upload(segs.data(), segs.size(), s);
+	int blocks = coop_blocks(k_panel_solve, 1024);
+	blocks = std::min(blocks, ctx().sm_count);
 	const i64 *a_ptr = G.ptr.ptr;
 	const int *a_src = G.src.ptr;
 	const i32 *a_val = G.val.ptr;
 	const int *a_order = G.order.ptr, *a_lp = G.level_ptr.ptr;
-	int nlevels = G.nlevels;
+	const SolveSegment *a_segs = d_segs.ptr;
+	int nsegs = (int) segs.size();
 	int4 *a_X = (int4 *) X;
 	Zp Fc = F;
-	void *args[] = {&a_ptr, &a_src, &a_val, &a_order, &a_lp, &nlevels, &a_X, &ld4, &R4, &TR, &Fc};
+	void *args[] = {&a_ptr, &a_src, &a_val, &a_order, &a_lp, &a_segs, &nsegs, &a_X, &ld4, &R4, &Fc};
 	GpuTimer tk;
 	tk.start();
-	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_panel_solve, dim3(blocks), dim3(256), args, 0, ctx().stream));
+	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_panel_solve, dim3(blocks), dim3(1024), args, 0, s));
 	LAUNCHED(1);
 	stats().pub.ms_k_panel_solve += tk.stop_ms();
 	Stats &st = stats();

@@ -134,3 +134,19 @@ def test_dense_rref_matches_oracle(product, prime, shape):
     for i in range(rank):
         for k in range(rank, m):
             assert packed[i, k] == W[i, qinv[k]]
+
+
+def test_device_prng_known_answers(product):
+    """the SHA-256 counter-mode streams generated on the device (prng.cu) against tests/Expected/prng of the reference"""
+    from test_oracle_pinned import PRNG_KAT
+    for prime, seed, seq, want in PRNG_KAT:
+        out = np.zeros(10, np.int32)
+        product.spasm_b200_prng_stream(prime, seed, seq, 10, abi.as_i32_p(out))
+        assert out.tolist() == want
+    # long streams against the oracle's implementation, including a 32-bit prime (rejection sampling path)
+    for prime in (3, 42013, 2147483629, 4294967291):
+        out = np.zeros(3000, np.int32)
+        product.spasm_b200_prng_stream(prime, 12345, 0, 3000, abi.as_i32_p(out))
+        ref = (C.c_int32 * 3000)()
+        oracle.lib().oracle_prng_stream(prime, 12345, 0, 3000, ref)
+        assert out.tolist() == list(ref)
