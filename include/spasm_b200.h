@@ -66,6 +66,10 @@ void  spasm_b200_flush_l2(void);             /* writes 512 MB: cold L2 for the n
  * for the known-answer test against tests/Expected/prng */
 void spasm_b200_prng_stream(int64_t prime, uint64_t seed, uint32_t seq, int count, int32_t *out_host);
 
+/* test hook: C (M x N) -= A (M x K) * B (K x N) mod prime on host row-major matrices, through the CUDA-core product
+ * (use_tensor = 0) or the tcgen05 int8 limb-split product (use_tensor = 1) */
+void spasm_b200_gemm_sub(int64_t prime, int M, int N, int K, int32_t *C, const int32_t *A, const int32_t *B, int use_tensor);
+
 /* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
  * round after round; returns their number.  Pass NULL to query the count. */
 int spasm_b200_last_pivot_pairs(int *rows, int *cols, int *round_start /* size nrounds+1 */);

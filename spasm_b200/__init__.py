@@ -31,6 +31,7 @@ EXTRA_PROTOTYPES = {
     "spasm_b200_free_csr": (None, [C.c_void_p]),
     "spasm_b200_echelonize_resident": (C.c_int, [C.c_void_p, abi.OptsP, C.POINTER(C.c_double)]),
     "spasm_b200_flush_l2": (None, []),
+    "spasm_b200_gemm_sub": (None, [C.c_int64, C.c_int, C.c_int, C.c_int, abi.i32_p, abi.i32_p, abi.i32_p, C.c_int]),
     "spasm_b200_prng_stream": (None, [C.c_int64, C.c_uint64, C.c_uint32, C.c_int, abi.i32_p]),
     "spasm_b200_last_pivot_pairs": (C.c_int, [abi.c_int_p, abi.c_int_p, abi.c_int_p]),
 }

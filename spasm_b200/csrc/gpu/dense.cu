@@ -91,6 +91,13 @@ void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ld
 {
 	if (M <= 0 || N <= 0 || K <= 0)
 		return;
+	/* Large products go to the tensor cores (umma_gemm.cu).  The rank-<=32 trailing updates of dense_rref
+	 * (d_K != NULL) stay on the CUDA cores: with K = 32 the tcgen05 kernel is all prologue/epilogue. */
+	if (!d_K && K >= 64 && (double) M * N * K >= 4e6 && umma_gemm_available(F)) {
+		umma_gemm_sub(C, ldc, A, lda, B, ldb, M, N, K, F);
+		stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
+		return;
+	}
 	dim3 grid(cdiv(N, GN), cdiv(M, GM));
 	k_gemm_sub<<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
 	LAUNCHED(1);

@@ -19,6 +19,10 @@ namespace sb {
  * If d_K != NULL the inner dimension is read from device memory (<= K). */
 void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F, const int *d_K = nullptr);
 
+/* the same product on the int8 tensor cores (umma_gemm.cu): tcgen05.mma kind::i8 on signed byte limbs */
+bool umma_gemm_available(const Zp &F);
+void umma_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F);
+
 struct RrefResult {
 	int rank = 0;
 	std::vector<int> pivcol;    /* pivot column of RREF row t, increasing */

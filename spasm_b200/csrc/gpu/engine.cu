@@ -89,10 +89,11 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 	double gemm_ms = 0;
 	DevBuf<i32> Ac;
 	for (DenseBlock &blk : blocks) {
-		Ac.ensure((size_t) rows * blk.rr);
+		const int lda = (blk.rr + 3) & ~3;      /* 16-byte aligned rows for the vector loads of the tensor-core staging */
+		Ac.ensure((size_t) rows * lda);
 		tg.start();
-		dense_gather_columns(B, ldB, rows, blk.d_pivcol.ptr, blk.rr, Ac.ptr, blk.rr);
-		dense_gemm_sub(B, ldB, Ac.ptr, blk.rr, blk.D.ptr, blk.ld, rows, Sm0, blk.rr, F);
+		dense_gather_columns(B, ldB, rows, blk.d_pivcol.ptr, blk.rr, Ac.ptr, lda);
+		dense_gemm_sub(B, ldB, Ac.ptr, lda, blk.D.ptr, blk.ld, rows, Sm0, blk.rr, F);
 		gemm_ms += tg.stop_ms();
 	}
 	RrefResult res = dense_rref(B, rows, Sm0, ldB, F);

@@ -150,3 +150,33 @@ def test_device_prng_known_answers(product):
         ref = (C.c_int32 * 3000)()
         oracle.lib().oracle_prng_stream(prime, 12345, 0, 3000, ref)
         assert out.tolist() == list(ref)
+
+
+@pytest.mark.parametrize("prime", [3, 257, 42013, 65537, 189812507, 2147483629, 4278124287])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (200, 300, 100), (1000, 517, 1000), (77, 1031, 33), (130, 64, 4100)])
+def test_modular_product_tensor_cores_vs_cuda_cores_vs_exact(product, prime, shape):
+    """C -= A*B mod p: the tcgen05 int8 limb-split kernel, the CUDA-core kernel and exact Python integers agree
+    bit for bit (1 limb for p=3, 2 for 42013, 3 for 65537, 4 for the 31/32-bit primes; ragged tile edges)."""
+    M, N, K = shape
+    rng = np.random.default_rng(prime % 997 + M + N + K)
+    half, mhalf = prime // 2, prime // 2 - prime + 1
+    A = rng.integers(mhalf, half + 1, size=(M, K), dtype=np.int64)
+    B = rng.integers(mhalf, half + 1, size=(K, N), dtype=np.int64)
+    C0 = rng.integers(mhalf, half + 1, size=(M, N), dtype=np.int64)
+    if K > 40:                                   # extreme values exercise the limb carries
+        A[0, :] = half
+        B[:, 0] = mhalf
+        A[1, :] = mhalf
+    exact = None
+    if M * N * K <= 8_000_000:               # exact Python integers are slow: big shapes compare the two kernels only
+        exact = (C0.astype(object) - A.astype(object).dot(B.astype(object))) % prime
+        exact = np.where(exact > half, exact - prime, exact).astype(np.int64)
+    out = {}
+    for use_tensor in (0, 1):
+        Cc = np.ascontiguousarray(C0, np.int32)
+        product.spasm_b200_gemm_sub(prime, M, N, K, abi.as_i32_p(Cc), abi.as_i32_p(np.ascontiguousarray(A, np.int32)),
+                                    abi.as_i32_p(np.ascontiguousarray(B, np.int32)), use_tensor)
+        out[use_tensor] = Cc.astype(np.int64)
+    if exact is not None:
+        assert np.array_equal(out[0], exact), "CUDA-core product differs from exact arithmetic"
+    assert np.array_equal(out[1], out[0]), "tensor-core product differs from the CUDA-core product"

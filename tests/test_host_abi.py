@@ -186,3 +186,12 @@ def test_default_options_match_reference(product):
     assert (o.enable_greedy_pivot_search, o.enable_tall_and_skinny, o.enable_dense, o.enable_GPLU, o.L, o.complete) == (True, True, True, True, False, False)
     assert (o.min_pivot_proportion, o.max_round, o.sparsity_threshold, o.tall_and_skinny_ratio) == (0.1, 3, 0.05, 5)
     assert (o.dense_block_size, o.low_rank_ratio, o.low_rank_start_weight) == (1000, 0.5, -1)
+
+
+def test_tensor_core_path_is_really_tcgen05():
+    """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTC*MMA (UTCIMMA for kind::i8), tcgen05.ld -> LDTM,
+    tcgen05.commit -> UTCBAR in the built library; no legacy HMMA/IMMA tensor path."""
+    sass = subprocess.run(["cuobjdump", "-sass", spasm_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCIMMA" in sass, "no tcgen05.mma kind::i8 in the SASS"
+    assert "LDTM" in sass and "UTCBAR" in sass
+    assert " IMMA." not in sass and " HMMA." not in sass
