@@ -76,8 +76,19 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 	timer.start();
 	cudaStream_t s = ctx().stream;
 	const int n = A.n, m = A.m;
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace] %-28s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	DevBuf<int> d_pinv((size_t) std::max(n, 1)), d_qinv((size_t) std::max(m, 1));
 	PivotCounts cnt = pivots_find(A, d_pinv.ptr, d_qinv.ptr, greedy);
+	lap("pivots_find");
 	int npiv = cnt.fl + cnt.flcol + cnt.greedy;
 	LOG("[pivots] Faugère-Lachartre: %d pivots found\n[pivots] ``Faugère-Lachartre on columns'': %d pivots found\n"
 	    "[pivots] greedy alternating cycle-free search: %d pivots found\n[pivots] %d pivots found\n",
@@ -104,10 +115,14 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 		Unew.m = m;
 		Unew.prime = A.prime;
 		DevBuf<int> scratch_qinv((size_t) m);
+		lap("select rows");
 		append_pivotal_rows(A, rows_tmp.ptr, npiv, d_pinv.ptr, Unew, scratch_qinv);
+		lap("U (column order)");
 		DepGraph Gnew;
 		depgraph_forward(Unew, Gnew);
+		lap("depgraph_forward");
 		depgraph_schedule(Gnew);
+		lap("depgraph_schedule");
 		/* 2. pivot columns by (level, column) -> final order of the new rows */
 		DevBuf<int> flags2((size_t) m), rows_ord((size_t) m), rows_sorted((size_t) npiv);
 		k_select_rows<<<cdiv(m, 256), 256, 0, s>>>(m, Gnew.order.ptr, d_qinv.ptr, flags2.ptr, rows_ord.ptr);
@@ -117,6 +132,7 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 			errx(1, "[spasm-b200] internal: pivot order mismatch");
 		bool first_rows = (E.U.n == 0);
 		append_pivotal_rows(A, rows_sorted.ptr, npiv, d_pinv.ptr, E.U, E.Uqinv);
+		lap("U (level order)");
 		h_rows.resize(npiv);
 		rows_sorted.download(h_rows.data(), (size_t) npiv, s);
 		sync();
@@ -139,6 +155,7 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 	for (int i = 0; i < n; i++)
 		if (h_pinv[i] < 0)
 			p[k++] = i;
+	lap("host permutation");
 	st.pub.ms_pivots += timer.stop_ms();
 	return npiv;
 }

@@ -384,6 +384,9 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		out.fl = fetch(counters.ptr + 0);
 	}
 
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t0 = spasm_wtime();
+	if (trace) { sync(); fprintf(stderr, "[trace]   FL %.3f ms\n", 1e3 * (spasm_wtime() - t0)); t0 = spasm_wtime(); }
 	/* --- FL on columns */
 	{
 		DevBuf<unsigned char> open((size_t) m), decided((size_t) n), closing((size_t) n);
@@ -408,6 +411,7 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		out.flcol = fetch(counters.ptr + 2);
 	}
 
+	if (trace) { sync(); fprintf(stderr, "[trace]   FL-columns %.3f ms\n", 1e3 * (spasm_wtime() - t0)); t0 = spasm_wtime(); }
 	/* --- greedy */
 	if (greedy) {
 		GpuTimer timer;

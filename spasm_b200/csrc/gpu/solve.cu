@@ -165,60 +165,107 @@ __global__ void k_rev_fill(int nnodes, const i64 *__restrict__ ptr, const int *_
 		rdst[atomicAdd(&cursor[src[k]], 1ull)] = c;
 }
 
-__global__ void k_kahn_seed(int nnodes, const int *__restrict__ indeg, int *order, int *level, int *tail)
+__global__ void k_kahn_seed(int nnodes, const int *__restrict__ indeg, int *order, unsigned long long *state, int *tail)
 {
 	int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= nnodes)
 		return;
-	if (indeg[c] == 0) {
+	state[c] = (unsigned long long) (unsigned) indeg[c];        /* level 0, all dependencies pending */
+	if (indeg[c] == 0)
 		order[atomicAdd(tail, 1)] = c;
-		level[c] = 0;
-	} else {
-		level[c] = -1;
-	}
 }
 
-/* persistent cooperative kernel: one frontier (= one level) per iteration */
-__global__ void k_kahn(const i64 *__restrict__ rptr, const int *__restrict__ rdst, int *indeg, int *order, int *level,
-                       int *tail, int *level_ptr, int *nlevels_out)
+/*
+ * Levels of the dependency DAG without a barrier per level ("asynchronous Kahn").
+ * order[] doubles as a work queue: slot t is claimed by exactly one thread (atomic ticket) which spins until the
+ * slot is filled, then releases the dependents of that node: level[c] = max(level[c], level[s] + 1) and, when the
+ * last dependency of c is released, c is appended to the queue.  Every node is appended exactly once (the graph
+ * is acyclic), so all n tickets terminate; the critical path is depth x (one atomic round trip) instead of
+ * depth x (two grid barriers).  A cycle (invalid input) would leave slots empty for ever: a spin budget turns
+ * that into an error flag.  The grid is sized to be co-resident (the spinning threads must all run).
+ */
+__global__ void k_kahn_async(int n, const i64 *__restrict__ rptr, const int *__restrict__ rdst, unsigned long long *state, int *order,
+                             int *level, int *tail, int *ticket, int *error, int *done)
 {
-	cg::grid_group grid = cg::this_grid();
-	int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-	int begin = 0, end = *tail, L = 0;
-	grid.sync();
-	while (begin < end) {
-		if (gtid == 0)
-			level_ptr[L] = begin;
-		for (int idx = begin + gtid; idx < end; idx += gsize) {
-			int s = order[idx];
-			for (i64 k = rptr[s]; k < rptr[s + 1]; k++) {
-				int c = rdst[k];
-				if (atomicSub(&indeg[c], 1) == 1) {
-					order[atomicAdd(tail, 1)] = c;
-					level[c] = L + 1;
+	/* One WARP per node (idle lanes that spin in the same warp as a working lane would steal its issue slots).
+	 * state[c] = (level so far << 32) | dependencies not yet released: one 64-bit CAS releases a dependency and
+	 * raises the level at once, so the lane that releases the last one knows the final level.  The dependents of
+	 * a node are released by the lanes in parallel.  The warp keeps one released node for itself (no queue round
+	 * trip on the critical path: a chain of the DAG is walked by one warp); the others go to the shared queue. */
+	const int lane = threadIdx.x & 31;
+	int next = -1;
+	for (;;) {
+		int s = next;
+		next = -1;
+		if (s < 0) {
+			if (lane == 0) {
+				const int t = atomicAdd(ticket, 1);
+				for (long spin = 0;; spin++) {
+					if (t < n) {
+						s = *((volatile int *) &order[t]);
+						if (s >= 0)
+							break;
+					}
+					if (*((volatile int *) done) >= n || *((volatile int *) error)) {
+						s = -2;
+						break;
+					}
+					if (spin > (1L << 24)) {
+						*error = 1;
+						s = -2;
+						break;
+					}
+					__nanosleep(200);
+				}
+			}
+			s = __shfl_sync(0xffffffffu, s, 0);
+			if (s < 0)
+				return;
+		}
+		const unsigned ls = (unsigned) (*((volatile unsigned long long *) &state[s]) >> 32);
+		const i64 b = rptr[s], e = rptr[s + 1];
+		if (lane == 0)
+			level[s] = (int) ls;
+		for (i64 k0 = b; k0 < e; k0 += 32) {
+			const i64 k = k0 + lane;
+			int released = -1;
+			if (k < e) {
+				const int c = rdst[k];
+				unsigned long long old = *((volatile unsigned long long *) &state[c]), assumed, upd;
+				do {
+					assumed = old;
+					unsigned lv = (unsigned) (assumed >> 32), cnt = (unsigned) assumed;
+					lv = lv > ls + 1 ? lv : ls + 1;
+					upd = ((unsigned long long) lv << 32) | (cnt - 1);
+					old = atomicCAS(&state[c], assumed, upd);
+				} while (old != assumed);
+				if ((unsigned) upd == 0)
+					released = c;
+			}
+			unsigned mask = __ballot_sync(0xffffffffu, released >= 0);
+			if (mask) {
+				int keep_lane = -1;
+				if (next < 0) {
+					keep_lane = __ffs(mask) - 1;
+					next = __shfl_sync(0xffffffffu, released, keep_lane);
+				}
+				if (released >= 0 && lane != keep_lane) {
+					const int pos = atomicAdd(tail, 1);
+					__threadfence();
+					*((volatile int *) &order[pos]) = released;
 				}
 			}
 		}
-		grid.sync();
-		int newend = *((volatile int *) tail);
-		grid.sync();
-		begin = end;
-		end = newend;
-		L++;
-	}
-	if (gtid == 0) {
-		level_ptr[L] = begin;
-		*nlevels_out = L;
+		if (lane == 0)
+			atomicAdd(done, 1);
 	}
 }
 
 __global__ void k_make_keys(int n, const int *__restrict__ order, const int *__restrict__ level, unsigned long long *keys)
 {
-	int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < n) {
-		int c = order[t];
-		keys[t] = ((unsigned long long) (unsigned) level[c] << 32) | (unsigned) c;
-	}
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < n)
+		keys[c] = ((unsigned long long) (unsigned) level[c] << 32) | (unsigned) c;
 }
 
 __global__ void k_keys_to_order(int n, const unsigned long long *__restrict__ keys, int *order)
@@ -228,9 +275,51 @@ __global__ void k_keys_to_order(int n, const unsigned long long *__restrict__ ke
 		order[t] = (int) (keys[t] & 0xffffffffull);
 }
 
+/* level_ptr[L] = first position in the sorted keys whose level is >= L (L = 0 .. nlevels) */
+__global__ void k_level_bounds(int n, const unsigned long long *__restrict__ keys, int nlevels, int *level_ptr)
+{
+	int L = blockIdx.x * blockDim.x + threadIdx.x;
+	if (L > nlevels)
+		return;
+	int lo = 0, hi = n;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if ((int) (keys[mid] >> 32) < L)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	level_ptr[L] = lo;
+}
+
+/* pending0[c] = dependencies of c whose source is not a level-0 node; seeds = level >= 1 nodes with pending0 == 0 */
+__global__ void k_flow_prepare(int n, const i64 *__restrict__ ptr, const int *__restrict__ src, const int *__restrict__ level,
+                               int *pending0, int *seeds, int *nseeds)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n)
+		return;
+	int cnt = 0;
+	for (i64 e = ptr[c]; e < ptr[c + 1]; e++)
+		cnt += level[src[e]] > 0;
+	pending0[c] = cnt;
+	if (level[c] >= 1 && cnt == 0)
+		seeds[atomicAdd(nseeds, 1)] = c;
+}
+
 void depgraph_schedule(DepGraph &G)
 {
 	cudaStream_t s = ctx().stream;
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace]     schedule/%-18s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	int n = G.nnodes;
 	G.level.alloc((size_t) n + 1);
 	G.order.alloc((size_t) n + 1);
@@ -239,37 +328,42 @@ void depgraph_schedule(DepGraph &G)
 	G.nlevels = 0;
 	if (n == 0)
 		return;
-	DevBuf<i64> rcnt((size_t) n + 1), rptr((size_t) n + 1);
-	DevBuf<int> indeg((size_t) n), rdst((size_t) std::max<i64>(G.ndeps, 1)), counters(2);
+	DevBuf<i64> rcnt((size_t) n + 1);
+	G.rptr.alloc((size_t) n + 1);
+	G.rdst.alloc((size_t) std::max<i64>(G.ndeps, 1));
+	DevBuf<i64> &rptr = G.rptr;
+	DevBuf<int> &rdst = G.rdst;
+	DevBuf<int> indeg((size_t) n), counters(4);
 	rcnt.zero(s);
 	counters.zero(s);
+	G.order.fill_byte(0xff, s);        /* empty queue slots */
 	k_rev_count<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, (unsigned long long *) rcnt.ptr, indeg);
 	exclusive_scan_i64(rcnt.ptr, rptr.ptr, (size_t) n + 1);
 	CUDA_CHECK(cudaMemcpyAsync(rcnt.ptr, rptr.ptr, ((size_t) n + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
 	k_rev_fill<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, (unsigned long long *) rcnt.ptr, rdst);
-	k_kahn_seed<<<cdiv(n, 256), 256, 0, s>>>(n, indeg, G.order, G.level, counters.ptr);
+	DevBuf<unsigned long long> state((size_t) n);
+	k_kahn_seed<<<cdiv(n, 256), 256, 0, s>>>(n, indeg, G.order, state.ptr, counters.ptr);
 	LAUNCHED(3);
 	KERNEL_CHECK();
+	lap("reverse graph");
 
-	int threads = 256;
-	int blocks = coop_blocks(k_kahn, threads);
-	const i64 *a_rptr = rptr.ptr;
-	const int *a_rdst = rdst.ptr;
-	int *a_indeg = indeg.ptr, *a_order = G.order.ptr, *a_level = G.level.ptr, *a_tail = counters.ptr;
-	int *a_lp = G.level_ptr.ptr, *a_nl = counters.ptr + 1;
-	void *args[] = {&a_rptr, &a_rdst, &a_indeg, &a_order, &a_level, &a_tail, &a_lp, &a_nl};
-	CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_kahn, dim3(blocks), dim3(threads), args, 0, s));
-	LAUNCHED(1);
-	int h[2];
-	CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+	{
+		int threads = 128;
+		int occ = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_kahn_async, threads, 0));
+		int blocks = std::max(1, std::min(occ, 4)) * ctx().sm_count;          /* co-resident: idle warps spin on the queue */
+		k_kahn_async<<<blocks, threads, 0, s>>>(n, rptr.ptr, rdst.ptr, state.ptr, G.order.ptr, G.level.ptr, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3);
+		LAUNCHED(1);
+		KERNEL_CHECK();
+	}
+	int h[4];
+	CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
 	sync();
-	if (h[0] != n)
-		errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d nodes scheduled): invalid U / qinv", h[0], n);
-	G.nlevels = h[1];
-	G.level_ptr_h.resize((size_t) G.nlevels + 1);
-	CUDA_CHECK(cudaMemcpyAsync(G.level_ptr_h.data(), G.level_ptr.ptr, ((size_t) G.nlevels + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+	lap("kahn");
+	if (h[3] != n || h[2] != 0)
+		errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d nodes scheduled): invalid U / qinv", h[3], n);
 
-	/* deterministic order inside each level: sort by (level, node) */
+	/* deterministic order inside each level: sort by (level, node); level boundaries by binary search on the keys */
 	DevBuf<unsigned long long> keys((size_t) n), keys2((size_t) n);
 	k_make_keys<<<cdiv(n, 256), 256, 0, s>>>(n, G.order, G.level, keys.ptr);
 	static DevBuf<char> tmp;
@@ -278,9 +372,25 @@ void depgraph_schedule(DepGraph &G)
 	tmp.ensure(bytes + 16);
 	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
 	k_keys_to_order<<<cdiv(n, 256), 256, 0, s>>>(n, keys2.ptr, G.order);
-	LAUNCHED(3);
-	KERNEL_CHECK();
+	unsigned long long last_key = 0;
+	CUDA_CHECK(cudaMemcpyAsync(&last_key, keys2.ptr + (n - 1), sizeof(last_key), cudaMemcpyDeviceToHost, s));
 	sync();
+	G.nlevels = (int) (last_key >> 32) + 1;
+	k_level_bounds<<<cdiv(G.nlevels + 1, 256), 256, 0, s>>>(n, keys2.ptr, G.nlevels, G.level_ptr.ptr);
+	LAUNCHED(4);
+	KERNEL_CHECK();
+	G.level_ptr_h.resize((size_t) G.nlevels + 1);
+	CUDA_CHECK(cudaMemcpyAsync(G.level_ptr_h.data(), G.level_ptr.ptr, ((size_t) G.nlevels + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+	sync();
+	/* dataflow schedule of the solve */
+	G.pending0.alloc((size_t) n);
+	G.seeds.alloc((size_t) n);
+	CUDA_CHECK(cudaMemsetAsync(counters.ptr, 0, sizeof(int), s));
+	k_flow_prepare<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, G.level, G.pending0.ptr, G.seeds.ptr, counters.ptr);
+	LAUNCHED(1);
+	G.nseeds = fetch(counters.ptr);
+	G.nscheduled = n - G.level_ptr_h[1];
+	lap("sort + bounds");
 	G.scheduled_deps = G.ndeps;
 }
 
@@ -347,6 +457,103 @@ k_panel_solve(const i64 *__restrict__ ptr, const int *__restrict__ src, const i3
 	}
 }
 
+/*
+ * Dataflow variant: no barrier between levels.  One CTA owns one column at a time: it computes the column for
+ * every right-hand side, publishes it (__threadfence), then releases the columns that depend on it by
+ * decrementing their pending counters; a CTA that releases a column keeps it as its next job (a chain of the DAG
+ * is walked by one CTA without a queue round trip), further released columns go to a shared queue that idle CTAs
+ * poll.  Sources (level-0 columns) are final from the start and are never scheduled.  The values do not depend
+ * on the schedule (each column is still written once, from final columns).
+ */
+__global__ void __launch_bounds__(256)
+k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+                   const i64 *__restrict__ rptr, const int *__restrict__ rdst, const int *__restrict__ level,
+                   int *pending, int *queue, int nseeds, int nscheduled, int *tail, int *ticket, int *done, int *error,
+                   int4 *X, int ld4, int R4, Zp F)
+{
+	__shared__ int s_node, s_next;
+	const int tid = threadIdx.x;
+	int next = -1;
+	for (;;) {
+		int c = next;
+		next = -1;
+		if (c < 0) {
+			if (tid == 0) {
+				const int t = atomicAdd(ticket, 1);
+				int got = -2;
+				for (long spin = 0;; spin++) {
+					if (t < nscheduled) {
+						got = *((volatile int *) &queue[t]);
+						if (got >= 0)
+							break;
+					}
+					if (*((volatile int *) done) >= nscheduled || *((volatile int *) error)) {
+						got = -2;
+						break;
+					}
+					if (spin > (1L << 24)) {
+						*error = 1;
+						got = -2;
+						break;
+					}
+					__nanosleep(100);
+				}
+				s_node = got;
+			}
+			__syncthreads();
+			c = s_node;
+			__syncthreads();
+			if (c < 0)
+				return;
+		}
+		/* the column, for all right-hand sides; dependencies are read around L1 (they were written by other SMs) */
+		{
+			const i64 e0 = ptr[c], e1 = ptr[c + 1];
+			int4 *Xc = X + (size_t) c * ld4;
+			for (int r = tid; r < R4; r += blockDim.x) {
+				int4 b = Xc[r];
+				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+				int pendingred = 0;
+				for (i64 e = e0; e < e1; e++) {
+					const i64 v = val[e];
+					const int4 xs = __ldcg(&X[(size_t) src[e] * ld4 + r]);
+					a0 -= v * xs.x;
+					a1 -= v * xs.y;
+					a2 -= v * xs.z;
+					a3 -= v * xs.w;
+					if (++pendingred == F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pendingred = 0;
+					}
+				}
+				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
+				Xc[r] = b;
+			}
+		}
+		__threadfence();
+		if (tid == 0)
+			s_next = -1;
+		__syncthreads();
+		/* release the dependents */
+		const i64 b = rptr[c], e = rptr[c + 1];
+		for (i64 k = b + tid; k < e; k += blockDim.x) {
+			const int d = rdst[k];
+			if (atomicSub(&pending[d], 1) == 1) {
+				if (atomicCAS(&s_next, -1, d) != -1) {
+					const int pos = atomicAdd(tail, 1);
+					__threadfence();
+					*((volatile int *) &queue[pos]) = d;
+				}
+			}
+		}
+		__syncthreads();
+		next = s_next;
+		if (tid == 0)
+			atomicAdd(done, 1);
+		__syncthreads();
+	}
+}
+
 void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 {
 	if (G.nlevels <= 1 || R <= 0)
@@ -355,6 +562,37 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		errx(1, "[spasm-b200] internal: panel leading dimension must be a multiple of 4");
 	int R4 = (R + 3) / 4, ld4 = ld / 4;
 	cudaStream_t s = ctx().stream;
+	static const bool use_levels = getenv("SPASM_B200_SOLVE_LEVELS") != NULL;
+	if (!use_levels && G.nscheduled > 0) {
+		int n = G.nnodes;
+		DevBuf<int> pending((size_t) n), queue((size_t) n + 1), counters(4);
+		CUDA_CHECK(cudaMemcpyAsync(pending.ptr, G.pending0.ptr, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		queue.fill_byte(0xff, s);
+		CUDA_CHECK(cudaMemcpyAsync(queue.ptr, G.seeds.ptr, (size_t) G.nseeds * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		int h_init[4] = {G.nseeds, 0, 0, 0};      /* tail, ticket, done, error */
+		CUDA_CHECK(cudaMemcpyAsync(counters.ptr, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
+		int occ = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, 256, 0));
+		int blocks = std::max(1, std::min(occ, 8)) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
+		GpuTimer tk;
+		tk.start();
+		k_panel_solve_flow<<<blocks, 256, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, G.level.ptr, pending.ptr, queue.ptr,
+		                                         G.nseeds, G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3,
+		                                         (int4 *) X, ld4, R4, F);
+		LAUNCHED(1);
+		KERNEL_CHECK();
+		stats().pub.ms_k_panel_solve += tk.stop_ms();
+		int h[4];
+		CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+		sync();
+		if (h[3] != 0 || h[2] != G.nscheduled)
+			errx(1, "[spasm-b200] internal: dataflow solve did not complete (%d of %d columns)", h[2], G.nscheduled);
+		Stats &st = stats();
+		st.pub.solve_batches += 1;
+		st.pub.solve_rows += R;
+		st.pub.solve_traffic_model += ((double) G.ndeps + 2.0 * G.nscheduled) * 4.0 * R;
+		return;
+	}
 	/* segments: a level is narrow when one CTA covers it in at most two passes */
 	std::vector<SolveSegment> segs;
 	const int narrow_items = getenv("SPASM_B200_NARROW_ITEMS") ? atoi(getenv("SPASM_B200_NARROW_ITEMS")) : 2048;

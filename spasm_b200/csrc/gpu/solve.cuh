@@ -43,6 +43,13 @@ struct DepGraph {
 	DevBuf<int> order;        /* nodes sorted by (level, index) */
 	DevBuf<int> level;        /* level of each node */
 	i64 scheduled_deps = 0;
+	/* dataflow schedule: reverse adjacency (node -> nodes that depend on it) and, per node, the number of its
+	 * dependencies that are not sources (level > 0) */
+	DevBuf<i64> rptr;
+	DevBuf<int> rdst;
+	DevBuf<int> pending0;
+	DevBuf<int> seeds;        /* nodes of level >= 1 all of whose dependencies are sources */
+	int nseeds = 0, nscheduled = 0;
 };
 
 /* deps of column c: (pivot column of row i, U[i][c]) for every row i of U holding c outside its pivot.
