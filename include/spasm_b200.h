@@ -37,6 +37,7 @@ struct spasm_b200_stats {
 	double gemm_int8_ops;         /* limb products actually issued to the int8 tensor pipe (0 when on CUDA cores) */
 	int64_t greedy_edges;         /* pivot-row entries traversed by the greedy search */
 	int64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe by the library */
+	int64_t nccl_bytes;           /* bytes received through NCCL collectives by this rank */
 	/* trace of the last spasm_echelonize call, for parity with the oracle */
 	int nrounds;
 	int found_FL[64], found_FLcol[64], found_greedy[64];
@@ -69,6 +70,15 @@ void spasm_b200_prng_stream(int64_t prime, uint64_t seed, uint32_t seq, int coun
 /* test hook: C (M x N) -= A (M x K) * B (K x N) mod prime on host row-major matrices, through the CUDA-core product
  * (use_tensor = 0) or the tcgen05 int8 limb-split product (use_tensor = 1) */
 void spasm_b200_gemm_sub(int64_t prime, int M, int N, int K, int32_t *C, const int32_t *A, const int32_t *B, int use_tensor);
+
+/* Multi-GPU (one process per GPU).  Rank 0 creates a 128-byte NCCL unique id, the caller distributes it (e.g.
+ * torch.distributed.broadcast), every rank calls spasm_b200_comm_init.  From then on spasm_echelonize shards the
+ * rows of its solve batches across the ranks and exchanges the dense blocks with ncclAllGather; every rank returns
+ * the same echelon form. */
+void spasm_b200_comm_unique_id(void *out128);
+void spasm_b200_comm_init(int rank, int world, const void *unique_id128);
+void spasm_b200_comm_destroy(void);
+int  spasm_b200_comm_world(void);
 
 /* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
  * round after round; returns their number.  Pass NULL to query the count. */

@@ -31,6 +31,10 @@ EXTRA_PROTOTYPES = {
     "spasm_b200_free_csr": (None, [C.c_void_p]),
     "spasm_b200_echelonize_resident": (C.c_int, [C.c_void_p, abi.OptsP, C.POINTER(C.c_double)]),
     "spasm_b200_flush_l2": (None, []),
+    "spasm_b200_comm_unique_id": (None, [C.c_void_p]),
+    "spasm_b200_comm_init": (None, [C.c_int, C.c_int, C.c_void_p]),
+    "spasm_b200_comm_destroy": (None, []),
+    "spasm_b200_comm_world": (C.c_int, []),
     "spasm_b200_gemm_sub": (None, [C.c_int64, C.c_int, C.c_int, C.c_int, abi.i32_p, abi.i32_p, abi.i32_p, C.c_int]),
     "spasm_b200_prng_stream": (None, [C.c_int64, C.c_uint64, C.c_uint32, C.c_int, abi.i32_p]),
     "spasm_b200_last_pivot_pairs": (C.c_int, [abi.c_int_p, abi.c_int_p, abi.c_int_p]),
@@ -45,7 +49,7 @@ class Stats(C.Structure):
                 ("ms_k_panel_solve", C.c_double), ("solve_bytes", C.c_double), ("solve_rows", C.c_int64),
                 ("solve_batches", C.c_int64), ("solve_traffic_model", C.c_double), ("gemm_fieldops", C.c_double),
                 ("gemm_int8_ops", C.c_double), ("greedy_edges", C.c_int64), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("nrounds", C.c_int), ("found_FL", C.c_int * 64), ("found_FLcol", C.c_int * 64),
+                ("d2h_bytes", C.c_int64), ("nccl_bytes", C.c_int64), ("nrounds", C.c_int), ("found_FL", C.c_int * 64), ("found_FLcol", C.c_int * 64),
                 ("found_greedy", C.c_int * 64), ("density", C.c_double * 64), ("finish", C.c_int), ("nblocks", C.c_int),
                 ("block_Sn", C.c_int * 4096), ("block_Sm", C.c_int * 4096), ("block_rr", C.c_int * 4096),
                 ("block_w", C.c_int * 4096), ("dag_depth", C.c_int)]

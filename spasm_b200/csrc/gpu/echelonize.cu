@@ -271,10 +271,7 @@ static void randomized_block(Engine &E, const DevCsr &A, const int *p, int n, in
 	}
 	d_rows.upload(rows.data(), rows.size(), s);
 	stats().pub.h2d_bytes += (i64) rows.size() * 4;
-	E.solve_combos(A, d_rows.ptr, d_coef.ptr, N, ww);
-	ldB = (E.Sm0 + 3) & ~3;
-	B.ensure((size_t) N * std::max(ldB, 4));
-	E.gather_q0(B.ptr, ldB);
+	E.block_from_combos(A, d_rows.ptr, d_coef.ptr, N, ww, B, ldB);
 }
 
 /* reference: src/spasm_echelonize.c:30-51 */
@@ -356,10 +353,8 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 		LOG("[echelonize/dense] Round %d. processing S[%d:%d] (%d x %d)\n", round, processed, processed + Sn, Sn, Sm);
 		DevBuf<int> d_rows;
 		d_rows.upload(p, (size_t) Sn, s);
-		E.solve_rows(A, d_rows.ptr, Sn, false);
-		int ldB = (E.Sm0 + 3) & ~3;
-		B.ensure((size_t) Sn * std::max(ldB, 4));
-		E.gather_q0(B.ptr, ldB);
+		int ldB;
+		E.block_from_rows(A, d_rows.ptr, Sn, B, ldB);
 		int rr = E.absorb_block(B.ptr, Sn, ldB);
 		record_block(Sn, Sm, rr, -1);
 		round += 1;

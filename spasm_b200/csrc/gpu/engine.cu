@@ -72,6 +72,32 @@ void Engine::solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef,
 	stats().pub.ms_solve += t.stop_ms();
 }
 
+void Engine::block_from_rows(const DevCsr &B, const int *d_rows, int R, DevBuf<i32> &out, int &ldB)
+{
+	ldB = std::max((Sm0 + 3) & ~3, 4);
+	int chunk, begin, end;
+	comm_slice(R, &chunk, &begin, &end);
+	out.ensure((size_t) chunk * comm_world() * ldB);
+	if (end > begin) {
+		solve_rows(B, d_rows + begin, end - begin, false);
+		gather_q0(out.ptr + (size_t) begin * ldB, ldB);
+	}
+	comm_allgather_rows(out.ptr, chunk, ldB);
+}
+
+void Engine::block_from_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, DevBuf<i32> &out, int &ldB)
+{
+	ldB = std::max((Sm0 + 3) & ~3, 4);
+	int chunk, begin, end;
+	comm_slice(N, &chunk, &begin, &end);
+	out.ensure((size_t) chunk * comm_world() * ldB);
+	if (end > begin) {
+		solve_combos(A, d_rows + (size_t) begin * w, d_coef + (size_t) begin * w, end - begin, w);
+		gather_q0(out.ptr + (size_t) begin * ldB, ldB);
+	}
+	comm_allgather_rows(out.ptr, chunk, ldB);
+}
+
 void Engine::gather_q0(i32 *S, int ldS)
 {
 	panel_gather_dense(panel, d_q0.ptr, Sm0, S, ldS);

@@ -49,10 +49,19 @@ struct Engine {
 	/* solve the rows `rows` (indices into B) against the structural U: results in panel */
 	void solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first);
 	void solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w);
+	/* dense block (R x Sm0, ld = ldB, room for world * chunk rows) of the rows / combinations reduced by the structural
+	 * pivots; with several ranks each one solves a slice and the slices are all-gathered */
+	void block_from_rows(const DevCsr &B, const int *d_rows, int R, DevBuf<i32> &out, int &ldB);
+	void block_from_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, DevBuf<i32> &out, int &ldB);
 	/* gather the q0 columns of the panel into a dense row-major block (R x Sm0, ld = ldS) */
 	void gather_q0(i32 *S, int ldS);
 	/* reduce a dense block by the dense rows found so far, echelonize it, keep its pivot rows. Returns rr. */
 	int absorb_block(i32 *B, int rows, int ldB);
 };
+
+int comm_world();
+int comm_rank();
+void comm_slice(int total, int *chunk, int *begin, int *end);
+void comm_allgather_rows(i32 *B, int chunk, int ld);
 
 }  // namespace sb

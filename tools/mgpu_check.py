@@ -1,0 +1,37 @@
+"""Multi-GPU parity check (run under torchrun): the echelon form computed cooperatively by all ranks must be identical,
+array for array, to the one each rank computes alone."""
+import os, sys, hashlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+local = int(os.environ.get("LOCAL_RANK", "0"))
+os.environ["SPASM_B200_DEVICE"] = str(local)
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import spasm_b200, oracle, util
+from spasm_b200 import synthetic, host, sharding
+L = spasm_b200.lib(); L.spasm_b200_set_verbose(0)
+cases = [synthetic.config1(0.1), synthetic.config2(0.1).transposed(), synthetic.config5(0.05), synthetic.config3(0.02)]
+opts = [{}, {}, {}, {"sparsity_threshold": 0.01}]
+def digest(f):
+    U = f.U
+    h = hashlib.sha256()
+    for k in "pjx": h.update(np.ascontiguousarray(U[k]).tobytes())
+    h.update(f.qinv.tobytes())
+    return f.rank, h.hexdigest()
+alone = []
+for t, o in zip(cases, opts):
+    A = host.compress(L, t); oracle.reset_rand()
+    alone.append(digest(host.echelonize(L, A, host.default_opts(L, **o))))
+sharding.init_comm(L, dist, device=torch.device("cuda", local))
+ok = True
+for (t, o), want in zip(zip(cases, opts), alone):
+    A = host.compress(L, t); oracle.reset_rand(); L.spasm_b200_reset_stats()
+    got = digest(host.echelonize(L, A, host.default_opts(L, **o)))
+    s = util.product_stats(L)
+    same = got == want
+    ok &= same
+    print(f"rank {dist.get_rank()}/{dist.get_world_size()} {t.name}: rank {got[0]} identical={same} nccl_bytes={s.nccl_bytes}", flush=True)
+v = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(v, op=dist.ReduceOp.MIN)
+if dist.get_rank() == 0: print("MULTI-GPU PARITY", "OK" if v.item() == 1.0 else "FAILED", flush=True)
+L.spasm_b200_comm_destroy(); dist.destroy_process_group()
