@@ -359,6 +359,338 @@ __global__ void __launch_bounds__(256, 8) k_greedy(GreedyArgs a)
 		atomicAdd(a.edges, my_edges);
 }
 
+/* ------------------------------------------------------------------ out-of-order commits
+ *
+ * The ordered kernel above serialises every commit behind all lower rows.  The sequential semantics only needs less:
+ *   (1) VISIBILITY: a greedy pivot (I, j) matters to row i only if I < i.  Greedy pivots are stored in qinv with a
+ *       tag bit; a row ignores tagged pivots whose owner is above it, so rows may commit in any order without
+ *       disturbing the rows below them.
+ *   (2) SAFETY: row i may commit as soon as its search is closed under the published pivots of lower rows and no
+ *       UNRESOLVED lower row can still produce a pivot that it would see: every unresolved lower row r publishes its
+ *       surviving candidate columns (a superset of whatever it will finally pick, only ever shrinking); if none of
+ *       them is marked (visited or survivor) in row i's bitmaps, a future pivot of r adds edges out of a column the
+ *       search of i never reaches, so i's result is final.  Otherwise i waits for those rows only.
+ * The lowest unresolved row never waits, so the scheme terminates, and the result is the sequential one.
+ */
+#define GREEDY_TAG 0x40000000
+#define SURV_SLOTS 8
+#define PEND_CAP 1024
+
+struct GreedyOooArgs {
+	int n, m, words, queue_cap, use_smem;
+	const i64 *Ap;
+	const int *Aj;
+	int *qinv, *pinv;
+	int *journal;
+	int *reserved;   /* journal slots handed out */
+	int *npiv;       /* journal slots published (every slot below is written) */
+	int *ticket;
+	int *status;     /* per row: 0 not initialised, 1 candidates published, 2 resolved */
+	int *surv;       /* per row: SURV_SLOTS candidate columns (-1 = none), or surv[0] == -2: too many to list */
+	int *hint;       /* every row below *hint is resolved */
+	unsigned *bitmaps;
+	int *queues;
+	unsigned long long *edges;
+};
+
+struct GreedyOooShared {
+	int row, head, tail, alive, npiv_local, np_now, scan, blocked, npend, changed;
+	int pend[PEND_CAP];
+};
+
+/* row owning the pivot of column j as seen by row i, or -1 */
+__device__ __forceinline__ int visible_owner(const int *qinv, int j, int i)
+{
+	int q = ld_volatile(&qinv[j]);
+	if (q < 0)
+		return -1;
+	if (q & GREEDY_TAG) {
+		q &= ~GREEDY_TAG;
+		return q < i ? q : -1;
+	}
+	return q;
+}
+
+__device__ __forceinline__ void ooo_mark(int c, unsigned *vis, unsigned *srv, int *queue, GreedyOooShared *sh)
+{
+	unsigned bit = 1u << (c & 31);
+	int word = c >> 5;
+	unsigned old = atomicOr(&vis[word], bit);
+	if (old & bit)
+		return;
+	unsigned olds = atomicAnd(&srv[word], ~bit);
+	if (olds & bit) {
+		atomicSub(&sh->alive, 1);
+		sh->changed = 1;
+	}
+	queue[atomicAdd(&sh->tail, 1)] = c;
+}
+
+__global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
+{
+	extern __shared__ unsigned dyn_smem[];
+	__shared__ GreedyOooShared sh;
+	const int tid = threadIdx.x, T = blockDim.x;
+	unsigned *vis = a.use_smem ? dyn_smem : a.bitmaps + (size_t) blockIdx.x * 2 * a.words;
+	unsigned *srv = vis + a.words;
+	int *queue = a.queues + (size_t) blockIdx.x * a.queue_cap;
+	unsigned long long my_edges = 0;
+
+	for (int w = tid; w < 2 * a.words; w += T)
+		vis[w] = 0;
+	if (tid == 0)
+		sh.scan = 0;
+	__syncthreads();
+
+	for (;;) {
+		if (tid == 0)
+			sh.row = atomicAdd(a.ticket, 1);
+		__syncthreads();
+		const int i = sh.row;
+		if (i >= a.n)
+			break;
+		if (ld_volatile(&a.pinv[i]) >= 0) {        /* pivotal since FL / FL-columns (pivots.c:192) */
+			if (tid == 0) {
+				__threadfence();
+				*((volatile int *) &a.status[i]) = 2;
+			}
+			__syncthreads();
+			continue;
+		}
+		const i64 rb = a.Ap[i], re = a.Ap[i + 1];
+		int *mysurv = a.surv + (size_t) i * SURV_SLOTS;
+
+		/* ---- scatter the row (pivots.c:198-215) and publish its candidate columns */
+		if (tid == 0) {
+			int np = ld_volatile(a.npiv);
+			__threadfence();
+			sh.npiv_local = np;
+			int tail = 0, alive = 0;
+			for (i64 k = rb; k < re; k++) {
+				int j = a.Aj[k];
+				unsigned bit = 1u << (j & 31);
+				int word = j >> 5;
+				if ((vis[word] | srv[word]) & bit)
+					continue;                   /* repeated column */
+				if (visible_owner(a.qinv, j, i) < 0) {
+					srv[word] |= bit;
+					if (alive < SURV_SLOTS)
+						mysurv[alive] = j;
+					alive += 1;
+				} else {
+					queue[tail++] = j;
+					vis[word] |= bit;
+				}
+			}
+			for (int t = alive; t < SURV_SLOTS; t++)
+				mysurv[t] = -1;
+			if (alive > SURV_SLOTS)
+				mysurv[0] = -2;                 /* too many to list: blocks the rows above until resolved */
+			__threadfence();
+			*((volatile int *) &a.status[i]) = 1;
+			sh.head = 0;
+			sh.tail = tail;
+			sh.alive = alive;
+			sh.npend = -1;                      /* pending list not built yet */
+			sh.changed = 0;
+		}
+		__syncthreads();
+
+		for (;;) {
+			/* ---- BFS along alternating paths (pivots.c:218-225) */
+			for (;;) {
+				const int head = sh.head, tail = sh.tail, alive = sh.alive;
+				__syncthreads();
+				if (head >= tail || alive <= 0)
+					break;
+				const int cnt = min(T, tail - head);
+				if (tid < cnt) {
+					int j = queue[head + tid];
+					int I = visible_owner(a.qinv, j, i);
+					if (I >= 0) {
+						i64 b = a.Ap[I], e = a.Ap[I + 1];
+						for (i64 k = b; k < e; k++)
+							ooo_mark(a.Aj[k], vis, srv, queue, &sh);
+						my_edges += (unsigned long long) (e - b);
+					}
+				}
+				if (tid == 0)
+					sh.head = head + cnt;
+				__syncthreads();
+			}
+			if (sh.alive <= 0)
+				break;                          /* no survivor: final */
+			/* ---- survivors that were reached are no candidates any more: shrink the published list */
+			if (sh.changed) {
+				if (tid < SURV_SLOTS) {
+					int c = mysurv[tid];
+					if (c >= 0 && !(srv[c >> 5] & (1u << (c & 31))))
+						*((volatile int *) &mysurv[tid]) = -1;
+				}
+				__syncthreads();
+				if (tid == 0)
+					sh.changed = 0;
+			}
+			/* ---- replay the pivots of lower rows published since the last look (pivots.c:260-274) */
+			if (tid == 0)
+				sh.np_now = ld_volatile(a.npiv);
+			__syncthreads();
+			const int np_now = sh.np_now, np_old = sh.npiv_local;
+			__syncthreads();
+			if (np_now != np_old) {
+				for (int t = np_old + tid; t < np_now; t += T) {
+					int j = ld_volatile(&a.journal[t]);
+					int owner = ld_volatile(&a.qinv[j]) & ~GREEDY_TAG;
+					if (owner >= i)
+						continue;               /* a pivot of a higher row: invisible to this row */
+					unsigned bit = 1u << (j & 31);
+					int word = j >> 5;
+					if (srv[word] & bit) {      /* a candidate became pivotal */
+						unsigned olds = atomicAnd(&srv[word], ~bit);
+						if (olds & bit) {
+							atomicSub(&sh.alive, 1);
+							sh.changed = 1;
+							atomicOr(&vis[word], bit);
+							queue[atomicAdd(&sh.tail, 1)] = j;
+						}
+					} else if (vis[word] & bit) {   /* a reached column became pivotal: expand its row */
+						i64 b = a.Ap[owner], e = a.Ap[owner + 1];
+						for (i64 k = b; k < e; k++)
+							ooo_mark(a.Aj[k], vis, srv, queue, &sh);
+						my_edges += (unsigned long long) (e - b);
+					}
+				}
+				if (tid == 0)
+					sh.npiv_local = np_now;
+				__syncthreads();
+				continue;                       /* close the search again */
+			}
+			/* ---- can any unresolved lower row still matter? */
+			if (sh.npend < 0) {                 /* first time: collect the unresolved rows below i */
+				if (tid == 0) {
+					sh.npend = 0;
+					sh.blocked = 0;
+					int k = max(sh.scan, ld_volatile(a.hint));
+					while (k < i && ld_volatile(&a.status[k]) == 2)
+						k++;
+					sh.scan = k;
+				}
+				__syncthreads();
+				for (int r = sh.scan + tid; r < i; r += T)
+					if (ld_volatile(&a.status[r]) != 2) {
+						int pos = atomicAdd(&sh.npend, 1);
+						if (pos < PEND_CAP)
+							sh.pend[pos] = r;
+					}
+				__syncthreads();
+				if (sh.npend > PEND_CAP) {      /* too many to track: look again later */
+					if (tid == 0)
+						sh.npend = -1;
+					__syncthreads();
+					__nanosleep(500);
+					continue;
+				}
+			}
+			if (tid == 0)
+				sh.blocked = 0;
+			__syncthreads();
+			const int npend = sh.npend;
+			for (int t = tid; t < npend; t += T) {
+				int r = sh.pend[t];
+				if (r < 0)
+					continue;
+				int st = ld_volatile(&a.status[r]);
+				if (st == 2) {
+					sh.pend[t] = -1;            /* resolved: its pivot, if any, is in the journal */
+					continue;
+				}
+				bool conflict = (st == 0);      /* candidates not published yet: unknown */
+				if (!conflict) {
+					const int *rs = a.surv + (size_t) r * SURV_SLOTS;
+					for (int q = 0; q < SURV_SLOTS && !conflict; q++) {
+						int c = ld_volatile(&rs[q]);
+						if (c == -2)
+							conflict = true;
+						else if (c >= 0 && ((vis[c >> 5] | srv[c >> 5]) & (1u << (c & 31))))
+							conflict = true;
+					}
+				}
+				if (conflict)
+					sh.blocked = 1;
+			}
+			__syncthreads();
+			/* a row seen as resolved may have published its pivot after our replay: look at the journal once more */
+			if (tid == 0)
+				sh.np_now = ld_volatile(a.npiv);
+			__syncthreads();
+			const bool fresh = (sh.np_now == sh.npiv_local);
+			const bool blocked = sh.blocked != 0;
+			__syncthreads();
+			if (!fresh)
+				continue;
+			if (!blocked)
+				break;                          /* commit */
+			__nanosleep(100);
+		}
+
+		/* ---- commit (pivots.c:227-255) */
+		if (tid == 0) {
+			if (sh.alive > 0) {
+				int j = -1;
+				for (i64 k = rb; k < re; k++) {     /* first survivor in row order (pivots.c:233-237) */
+					int c = a.Aj[k];
+					if (srv[c >> 5] & (1u << (c & 31))) {
+						j = c;
+						break;
+					}
+				}
+				a.pinv[i] = j;
+				*((volatile int *) &a.qinv[j]) = i | GREEDY_TAG;
+				__threadfence();
+				int pos = atomicAdd(a.reserved, 1);
+				*((volatile int *) &a.journal[pos]) = j;
+				__threadfence();
+				while (ld_volatile(a.npiv) != pos)
+					;                           /* publish in slot order: readers assume every slot below npiv is written */
+				*((volatile int *) a.npiv) = pos + 1;
+			}
+			__threadfence();
+			*((volatile int *) &a.status[i]) = 2;
+			if (sh.npend >= 0 && sh.scan >= 0) {
+				/* if everything below was resolved, move the hint */
+				bool all = true;
+				for (int t = 0; t < sh.npend && all; t++)
+					all = sh.pend[t] < 0;
+				if (all && sh.alive > 0)
+					atomicMax(a.hint, i + 1);
+			}
+		}
+		__syncthreads();
+
+		/* ---- reset the bitmaps (pivots.c:276-285) */
+		for (i64 k = rb + tid; k < re; k += T) {
+			int j = a.Aj[k];
+			atomicAnd(&vis[j >> 5], ~(1u << (j & 31)));
+			atomicAnd(&srv[j >> 5], ~(1u << (j & 31)));
+		}
+		const int tail = sh.tail;
+		for (int t = tid; t < tail; t += T) {
+			int j = queue[t];
+			atomicAnd(&vis[j >> 5], ~(1u << (j & 31)));
+		}
+		__syncthreads();
+	}
+	if (my_edges)
+		atomicAdd(a.edges, my_edges);
+}
+
+__global__ void k_strip_tags(int m, int *qinv)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < m && qinv[j] >= 0)
+		qinv[j] &= ~GREEDY_TAG;
+}
+
 /* ============================================================ driver */
 
 PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
@@ -456,19 +788,48 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		DevBuf<unsigned long long> edges(1);
 		status.zero(s);
 		edges.zero(s);
-		CUDA_CHECK(cudaMemsetAsync(counters.ptr + 3, 0, 4 * sizeof(int), s));
-		a.journal = journal.ptr;
-		a.npiv = counters.ptr + 3;
-		a.found = counters.ptr + 4;
-		a.ticket = counters.ptr + 5;
-		a.hint = counters.ptr + 6;
-		a.status = status.ptr;
-		a.bitmaps = bitmaps.ptr;
-		a.queues = queues.ptr;
-		a.edges = edges.ptr;
+		CUDA_CHECK(cudaMemsetAsync(counters.ptr + 3, 0, 5 * sizeof(int), s));
+		static const bool ordered = getenv("SPASM_B200_GREEDY_ORDERED") != NULL;
 		GpuTimer tk;
-		tk.start();
-		k_greedy<<<blocks, threads, smem, s>>>(a);
+		if (ordered || n >= GREEDY_TAG) {
+			a.journal = journal.ptr;
+			a.npiv = counters.ptr + 3;
+			a.found = counters.ptr + 4;
+			a.ticket = counters.ptr + 5;
+			a.hint = counters.ptr + 6;
+			a.status = status.ptr;
+			a.bitmaps = bitmaps.ptr;
+			a.queues = queues.ptr;
+			a.edges = edges.ptr;
+			tk.start();
+			k_greedy<<<blocks, threads, smem, s>>>(a);
+		} else {
+			GreedyOooArgs o;
+			o.n = n; o.m = m; o.words = a.words; o.queue_cap = a.queue_cap; o.use_smem = a.use_smem;
+			o.Ap = A.p; o.Aj = A.j; o.qinv = d_qinv; o.pinv = d_pinv;
+			DevBuf<int> surv((size_t) n * SURV_SLOTS);
+			o.journal = journal.ptr;
+			o.npiv = counters.ptr + 3;
+			o.reserved = counters.ptr + 4;
+			o.ticket = counters.ptr + 5;
+			o.hint = counters.ptr + 6;
+			o.status = status.ptr;
+			o.surv = surv.ptr;
+			o.bitmaps = bitmaps.ptr;
+			o.queues = queues.ptr;
+			o.edges = edges.ptr;
+			if (smem > 0)
+				CUDA_CHECK(cudaFuncSetAttribute(k_greedy_ooo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			int occ2 = 0;
+			CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_greedy_ooo, threads, smem));
+			if (occ2 < 1)
+				errx(1, "[spasm-b200] greedy pivot search kernel does not fit");
+			int blocks2 = std::min(blocks, std::min(occ2, per_sm) * ctx().sm_count);
+			tk.start();
+			k_greedy_ooo<<<blocks2, threads, smem, s>>>(o);
+			k_strip_tags<<<cdiv(m, 256), 256, 0, s>>>(m, d_qinv);
+			LAUNCHED(1);
+		}
 		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_greedy += tk.stop_ms();
