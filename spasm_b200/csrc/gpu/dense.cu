@@ -145,6 +145,24 @@ void dense_gather_rows(const i32 *src, int lds, const int *d_rows, int nrows, in
 	KERNEL_CHECK();
 }
 
+__global__ void k_scatter_rows_cols(const i32 *__restrict__ src, int lds, const int *__restrict__ rows, int nrows,
+                                    const int *__restrict__ cols, int ncols, i32 *dst, int ldd)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+	if (c < ncols && t < nrows)
+		dst[(size_t) t * ldd + cols[c]] = src[(size_t) rows[t] * lds + c];
+}
+
+void dense_scatter_rows(const i32 *src, int lds, const int *d_rows, int nrows, const int *d_cols, int ncols, i32 *dst, int ldd)
+{
+	if (nrows <= 0 || ncols <= 0)
+		return;
+	dim3 grid(cdiv(ncols, 256), nrows);
+	k_scatter_rows_cols<<<grid, 256, 0, ctx().stream>>>(src, lds, d_rows, nrows, d_cols, ncols, dst, ldd);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+}
+
 /* ================================================================== panel factorisation */
 
 #define NB 32
@@ -154,6 +172,7 @@ struct PanelInfo {
 	int k;
 	int prow[NB];
 	int pcol[NB];
+	i32 Minv[NB][NB];      /* inverse of S[prow, c0 + pcol] */
 };
 
 /*
@@ -283,25 +302,10 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 		__syncthreads();
 	}
 
-	/* --- multipliers */
-	for (int idx = tid; idx < n * NB; idx += T) {
-		int i = idx / NB, t = idx % NB;
-		i32 w = 0;
-		if (t < k) {
-			int mine = -1;
-			for (int s = 0; s < k; s++)
-				if (s_prow[s] == i)
-					mine = s;
-			if (mine >= 0) {
-				w = zp_reduce((i64) (mine == t) - Mw[mine][NB + t], F);
-			} else {
-				i64 acc = 0;
-				for (int s = 0; s < k; s++)
-					acc = zp_reduce(acc + (i64) zp_mul(S[(size_t) i * ld + c0 + s_pcol[s]], (i32) Mw[s][NB + t], F), F);
-				w = (i32) acc;
-			}
-		}
-		W[(size_t) i * NB + t] = w;
+	/* --- hand M^-1 to the multiplier kernel (the n x k x k product is spread over the whole GPU) */
+	for (int idx = tid; idx < NB * NB; idx += T) {
+		int s = idx / NB, t = idx % NB;
+		info->Minv[s][t] = (s < k && t < k) ? (i32) Mw[s][NB + t] : 0;
 	}
 	if (tid < k) {
 		info->prow[tid] = s_prow[tid];
@@ -312,6 +316,49 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 	__syncthreads();
 	if (tid == 0)
 		*rank_dev = r0 + k;
+}
+
+/* W[i][t] = sum_s S[i][c0 + pcol[s]] * Minv[s][t]   (rows of the panel's own pivots: (s == t) - Minv[s][t]); one thread per (i, t) */
+__global__ void __launch_bounds__(256)
+k_rref_multipliers(const i32 *__restrict__ S, int ld, int n, int c0, const PanelInfo *__restrict__ info, i32 *W, Zp F)
+{
+	__shared__ i32 sMinv[NB][NB + 1];
+	__shared__ int s_prow[NB], s_pcol[NB];
+	const int k = info->k;
+	if (k == 0)
+		return;
+	for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x)
+		sMinv[idx / NB][idx % NB] = info->Minv[idx / NB][idx % NB];
+	if (threadIdx.x < NB) {
+		s_prow[threadIdx.x] = info->prow[threadIdx.x];
+		s_pcol[threadIdx.x] = info->pcol[threadIdx.x];
+	}
+	__syncthreads();
+	const int t = threadIdx.x % NB;
+	for (int i = blockIdx.x * (blockDim.x / NB) + threadIdx.x / NB; i < n; i += gridDim.x * (blockDim.x / NB)) {
+		i32 w = 0;
+		if (t < k) {
+			int mine = -1;
+			for (int s = 0; s < k; s++)
+				if (s_prow[s] == i)
+					mine = s;
+			if (mine >= 0) {
+				w = zp_reduce((i64) (mine == t) - (i64) sMinv[mine][t], F);
+			} else {
+				i64 acc = 0;
+				int pending = 0;
+				for (int s = 0; s < k; s++) {
+					acc += (i64) S[(size_t) i * ld + c0 + s_pcol[s]] * (i64) sMinv[s][t];
+					if (++pending == F.delay) {
+						acc = zp_reduce(acc, F);
+						pending = 0;
+					}
+				}
+				w = zp_reduce(acc, F);
+			}
+		}
+		W[(size_t) i * NB + t] = w;
+	}
 }
 
 /* P[t][j] = S[prow[t]][c0 + j] */
@@ -345,9 +392,10 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 	for (int c0 = 0; c0 < m; c0 += NB) {
 		int width = m - c0;
 		k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, W.ptr, info.ptr, scratch.ptr, use_smem, F);
+		k_rref_multipliers<<<std::min(cdiv(n, 8), 148u * 4), 256, 0, s>>>(S, ld, n, c0, info.ptr, W.ptr, F);
 		dim3 g(cdiv(width, 256), NB);
 		k_copy_pivot_rows<<<g, 256, 0, s>>>(S, ld, c0, width, info.ptr, P.ptr, m);
-		LAUNCHED(2);
+		LAUNCHED(3);
 		dense_gemm_sub(S + c0, ld, W.ptr, NB, P.ptr, m, n, width, NB, F, &info.ptr->k);
 		if (++panels % 8 == 0 && fetch(rank_dev.ptr) >= n)
 			break;

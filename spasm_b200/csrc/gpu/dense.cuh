@@ -37,6 +37,9 @@ void dense_gather_columns(const i32 *src, int lds, int rows, const int *d_cols, 
 /* dst[t*ldd + :] = src[rows[t]*lds + :]  (width entries) */
 void dense_gather_rows(const i32 *src, int lds, const int *d_rows, int nrows, int width, i32 *dst, int ldd);
 
+/* dst[t*ldd + cols[c]] = src[rows[t]*lds + c]  for c < ncols (rows of a column-compacted matrix expanded back) */
+void dense_scatter_rows(const i32 *src, int lds, const int *d_rows, int nrows, const int *d_cols, int ncols, i32 *dst, int ldd);
+
 /* sparse rows (reference: src/spasm_echelonize.c:192-223, update_U_after_rref): for each of the nrows rows of D
  * (ld), the entries on columns c with skip[c] == 0 that are non-zero, as (colmap[c], value), by increasing c,
  * preceded by (colmap[pivcol[t]], 1).  Output CSR arrays on the device. */

@@ -297,6 +297,107 @@ static bool test_completion(Engine &E, const DevCsr &A, const int *p, int n)
 	return rr == 0;
 }
 
+/* ------------------------------------------------------------------ solve-ahead
+ *
+ * The elimination of a block by the STRUCTURAL pivots does not depend on the dense rows found by the earlier blocks
+ * (those are applied afterwards, as dense products).  So the structural solves of several consecutive blocks can
+ * share one pass over the pivot DAG, whose depth -- not its size -- is what a pass costs.
+ *   - finish_dense: the rows of all blocks are known in advance: they are solved in large batches.
+ *   - finish_lowrank: the rows of the next blocks depend on rand(), on the block sizes and on the weight, which the
+ *     reference only knows after each block.  We PREDICT them (every block finds as many pivots as it has rows, the
+ *     weight does not change: the normal course), peek at the corresponding glibc rand() draws, and solve the
+ *     predicted blocks together.  rand() is then rewound; each block consumes its draws for real when it is
+ *     processed, exactly like the reference, and if the prediction fails at some block the remaining predicted
+ *     blocks are discarded and recomputed.  The result is identical to the block-by-block course.
+ */
+struct RandSnapshot {
+	char *where = nullptr;
+	char saved[256];
+	size_t bytes = 0;
+};
+
+/* glibc keeps the state of rand()/random() in a table whose first word encodes the generator type and the position
+ * of its pointers whenever another table is installed (initstate/setstate).  Installing a temporary table therefore
+ * makes the live state a plain, copyable array. */
+static bool rand_snapshot(RandSnapshot &snap)
+{
+	static char scratch[256];
+	char *old = initstate(1, scratch, sizeof(scratch));
+	if (old == NULL)
+		return false;
+	static const size_t size_of_type[5] = {8, 32, 64, 128, 256};
+	int type = (int) (((const int32_t *) old)[0] % 5);
+	if (type < 0 || type > 4) {
+		setstate(old);
+		return false;
+	}
+	snap.where = old;
+	snap.bytes = size_of_type[type];
+	memcpy(snap.saved, old, snap.bytes);
+	setstate(old);
+	return true;
+}
+
+static void rand_restore(const RandSnapshot &snap)
+{
+	static char scratch[256];
+	initstate(1, scratch, sizeof(scratch));       /* park the generator elsewhere while its table is rewritten */
+	memcpy(snap.where, snap.saved, snap.bytes);
+	setstate(snap.where);
+}
+
+/* does snapshot/restore really rewind rand() on this libc?  (checked once; without it blocks are solved one by one) */
+static bool rand_rewind_works()
+{
+	static int known = -1;
+	if (known >= 0)
+		return known;
+	RandSnapshot s0;
+	known = 0;
+	if (!rand_snapshot(s0))
+		return false;
+	int a1 = rand(), a2 = rand(), a3 = rand();
+	rand_restore(s0);
+	int b1 = rand(), b2 = rand(), b3 = rand();
+	rand_restore(s0);
+	known = (a1 == b1 && a2 == b2 && a3 == b3);
+	return known;
+}
+
+struct AheadBlock { int Sn, n, w; };          /* predicted shape of a low-rank block */
+
+/* The dense blocks (reduced by the structural pivots) of several predicted low-rank blocks, stacked in `out`
+ * (block b starts at row offset[b]).  rand() is left untouched (peek). */
+static void randomized_blocks_ahead(Engine &E, const DevCsr &A, const int *p, const std::vector<AheadBlock> &plan,
+                                    DevBuf<i32> &out, int &ldB, std::vector<int> &offset)
+{
+	cudaStream_t s = ctx().stream;
+	RandSnapshot snap;
+	rand_snapshot(snap);
+	int w = plan[0].w;
+	size_t total = 0;
+	offset.clear();
+	for (const AheadBlock &b : plan) {
+		offset.push_back((int) total);
+		total += b.Sn;
+	}
+	std::vector<int> rows(total * w);
+	DevBuf<i32> d_coef(total * w);
+	size_t at = 0;
+	for (const AheadBlock &b : plan) {
+		for (int k = 0; k < b.Sn; k++)
+			for (int t = 0; t < w; t++)
+				rows[(at + k) * w + t] = p[rand() % b.n];
+		prng_combo_coefficients(E.prime, b.Sn, w, d_coef.ptr + at * w);     /* streams are seeded per row OF ITS BLOCK */
+		at += b.Sn;
+	}
+	rand_restore(snap);
+	DevBuf<int> d_rows;
+	d_rows.upload(rows.data(), rows.size(), s);
+	stats().pub.h2d_bytes += (i64) rows.size() * 4;
+	E.block_from_combos(A, d_rows.ptr, d_coef.ptr, (int) total, w, out, ldB);
+}
+
 /* reference: src/spasm_echelonize.c:315-379 */
 static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
 {
@@ -305,7 +406,12 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 	LOG("[echelonize/dense/low-rank] processing dense schur complement of dimension %d x %d; block size=%d\n", n, Sm, opts->dense_block_size);
 	int rank_ub = spasm_min(n, Sm);
 	int w = (opts->low_rank_start_weight < 0) ? (int) ceil(-log(0.01) * n / rank_ub) : (int) opts->low_rank_start_weight;
-	DevBuf<i32> B;
+	DevBuf<i32> B, ahead;
+	std::vector<AheadBlock> plan;     /* predicted blocks already solved, plan[next_ahead] is the next one */
+	std::vector<int> ahead_offset;
+	size_t next_ahead = 0;
+	int ahead_ld = 0;
+	static const bool no_ahead = getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
 	int round = 0;
 	for (;;) {
 		int Sn = spasm_min(rank_ub, opts->dense_block_size);
@@ -313,8 +419,44 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 			break;
 		LOG("[echelonize/dense/low-rank] Round %d. Weight %d. Processing chunk (%d x %d)\n", round, w, Sn, Sm);
 		int ldB;
-		randomized_block(E, A, p, n, Sn, w, B, ldB);
-		int rr = E.absorb_block(B.ptr, Sn, ldB);
+		i32 *block = nullptr;
+		if (next_ahead < plan.size() && plan[next_ahead].Sn == Sn && plan[next_ahead].n == n && plan[next_ahead].w == w) {
+			/* the prediction holds: consume this block's rand() draws like the reference, use the solved rows */
+			for (i64 t = 0; t < (i64) Sn * w; t++)
+				(void) rand();
+			block = ahead.ptr + (size_t) ahead_offset[next_ahead] * ahead_ld;
+			ldB = ahead_ld;
+			next_ahead++;
+		} else {
+			plan.clear();
+			next_ahead = 0;
+			if (w > 0 && !no_ahead && rand_rewind_works()) {
+				/* predict: every block has full rank and keeps the weight */
+				int n2 = n, ub2 = rank_ub;
+				size_t rows_ahead = 0;
+				const size_t row_budget = (size_t) 8 * opts->dense_block_size;
+				while (ub2 > 0 && rows_ahead < row_budget && (size_t) (plan.size() + 1) * w * opts->dense_block_size < ((size_t) 1 << 28)) {
+					int sn2 = spasm_min(ub2, opts->dense_block_size);
+					plan.push_back({sn2, n2, w});
+					rows_ahead += sn2;
+					n2 -= sn2;
+					ub2 -= sn2;
+				}
+			}
+			if (plan.size() > 1) {
+				randomized_blocks_ahead(E, A, p, plan, ahead, ahead_ld, ahead_offset);
+				for (i64 t = 0; t < (i64) Sn * w; t++)
+					(void) rand();
+				block = ahead.ptr;
+				ldB = ahead_ld;
+				next_ahead = 1;
+			} else {
+				plan.clear();
+				randomized_block(E, A, p, n, Sn, w, B, ldB);
+				block = B.ptr;
+			}
+		}
+		int rr = E.absorb_block(block, Sn, ldB);
 		record_block(Sn, Sm, rr, w);
 		if (rr == 0) {
 			if (test_completion(E, A, p, n))
@@ -346,16 +488,28 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 	bool lowrank_mode = false;
 	int rank_ub = spasm_min(A.n - E.rank(), A.m - E.rank());
 	DevBuf<i32> B;
+	int ahead_begin = 0, ahead_end = 0, ldB = 0;          /* rows [ahead_begin, ahead_end) of p are solved and sit in B */
+	const int base = processed;
+	const int *p0 = p;
+	static const bool no_ahead = getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
 	for (;;) {
 		int Sn = spasm_min(opts->dense_block_size, n - processed);
 		if (Sn <= 0)
 			break;
 		LOG("[echelonize/dense] Round %d. processing S[%d:%d] (%d x %d)\n", round, processed, processed + Sn, Sn, Sm);
-		DevBuf<int> d_rows;
-		d_rows.upload(p, (size_t) Sn, s);
-		int ldB;
-		E.block_from_rows(A, d_rows.ptr, Sn, B, ldB);
-		int rr = E.absorb_block(B.ptr, Sn, ldB);
+		if (processed >= ahead_end) {
+			/* structural solves of the next blocks in one batch (bounded by the memory of the stacked blocks) */
+			size_t per_row = (size_t) std::max((E.Sm0 + 3) & ~3, 4) * sizeof(i32);
+			size_t max_rows = std::max<size_t>((size_t) Sn, ((size_t) 12 << 30) / per_row);
+			int take = no_ahead ? Sn : (int) std::min<size_t>((size_t) (n - processed), max_rows);
+			take = std::max(Sn, take - take % opts->dense_block_size);
+			DevBuf<int> d_rows;
+			d_rows.upload(p0 + (processed - base), (size_t) take, s);
+			E.block_from_rows(A, d_rows.ptr, take, B, ldB);
+			ahead_begin = processed;
+			ahead_end = processed + take;
+		}
+		int rr = E.absorb_block(B.ptr + (size_t) (processed - ahead_begin) * ldB, Sn, ldB);
 		record_block(Sn, Sm, rr, -1);
 		round += 1;
 		processed += Sn;

@@ -78,9 +78,11 @@ void Engine::block_from_rows(const DevCsr &B, const int *d_rows, int R, DevBuf<i
 	int chunk, begin, end;
 	comm_slice(R, &chunk, &begin, &end);
 	out.ensure((size_t) chunk * comm_world() * ldB);
-	if (end > begin) {
-		solve_rows(B, d_rows + begin, end - begin, false);
-		gather_q0(out.ptr + (size_t) begin * ldB, ldB);
+	const int cap = panel_capacity(m);
+	for (int at = begin; at < end; at += cap) {
+		int R2 = std::min(cap, end - at);
+		solve_rows(B, d_rows + at, R2, false);
+		gather_q0(out.ptr + (size_t) at * ldB, ldB);
 	}
 	comm_allgather_rows(out.ptr, chunk, ldB);
 }
@@ -91,9 +93,11 @@ void Engine::block_from_combos(const DevCsr &A, const int *d_rows, const i32 *d_
 	int chunk, begin, end;
 	comm_slice(N, &chunk, &begin, &end);
 	out.ensure((size_t) chunk * comm_world() * ldB);
-	if (end > begin) {
-		solve_combos(A, d_rows + (size_t) begin * w, d_coef + (size_t) begin * w, end - begin, w);
-		gather_q0(out.ptr + (size_t) begin * ldB, ldB);
+	const int cap = panel_capacity(m);
+	for (int at = begin; at < end; at += cap) {
+		int N2 = std::min(cap, end - at);
+		solve_combos(A, d_rows + (size_t) at * w, d_coef + (size_t) at * w, N2, w);
+		gather_q0(out.ptr + (size_t) at * ldB, ldB);
 	}
 	comm_allgather_rows(out.ptr, chunk, ldB);
 }
@@ -122,7 +126,32 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 		dense_gemm_sub(B, ldB, Ac.ptr, lda, blk.D.ptr, blk.ld, rows, Sm0, blk.rr, F);
 		gemm_ms += tg.stop_ms();
 	}
-	RrefResult res = dense_rref(B, rows, Sm0, ldB, F);
+	/* Echelonize on the columns that are not pivotal yet only: after the reduction the block is zero on the pivot
+	 * columns of the earlier blocks, and panels made of such columns would be factorised for nothing.  The block is
+	 * compacted (gather of the remaining columns), echelonized, and its pivot rows are expanded back to the q0 space. */
+	int remaining = Sm0 - dense_rank;
+	DevBuf<i32> Bc;
+	const i32 *src = B;
+	int lds = ldB;
+	std::vector<int> cols;            /* compact column -> q0 column */
+	DevBuf<int> d_cols;
+	bool compact = !blocks.empty();
+	if (compact) {
+		std::vector<char> taken((size_t) Sm0, 0);
+		for (DenseBlock &blk : blocks)
+			for (int cpiv : blk.pivcol)
+				taken[cpiv] = 1;
+		cols.reserve(remaining);
+		for (int cidx = 0; cidx < Sm0; cidx++)
+			if (!taken[cidx])
+				cols.push_back(cidx);
+		d_cols.upload(cols.data(), cols.size(), s);
+		lds = std::max((remaining + 3) & ~3, 4);
+		Bc.alloc((size_t) rows * lds);
+		dense_gather_columns(B, ldB, rows, d_cols.ptr, remaining, Bc.ptr, lds);
+		src = Bc.ptr;
+	}
+	RrefResult res = dense_rref(const_cast<i32 *>(src), rows, compact ? remaining : Sm0, lds, F);
 	if (res.rank > 0) {
 		DenseBlock blk;
 		blk.rr = res.rank;
@@ -130,12 +159,20 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 		blk.D.alloc((size_t) blk.rr * blk.ld);
 		DevBuf<int> d_rows;
 		d_rows.upload(res.pivrow.data(), res.pivrow.size(), s);
-		dense_gather_rows(B, ldB, d_rows.ptr, blk.rr, Sm0, blk.D.ptr, blk.ld);
-		blk.pivcol = res.pivcol;
+		if (compact) {
+			blk.D.zero(s);
+			dense_scatter_rows(src, lds, d_rows.ptr, blk.rr, d_cols.ptr, remaining, blk.D.ptr, blk.ld);
+			blk.pivcol.resize(res.rank);
+			for (int t2 = 0; t2 < res.rank; t2++)
+				blk.pivcol[t2] = cols[res.pivcol[t2]];
+		} else {
+			dense_gather_rows(src, lds, d_rows.ptr, blk.rr, Sm0, blk.D.ptr, blk.ld);
+			blk.pivcol = res.pivcol;
+		}
 		blk.d_pivcol.upload(blk.pivcol.data(), blk.pivcol.size(), s);
 		std::vector<unsigned char> own((size_t) Sm0, 0);
-		for (int c : blk.pivcol)
-			own[c] = 1;
+		for (int cpiv : blk.pivcol)
+			own[cpiv] = 1;
 		blk.d_own.upload(own.data(), own.size(), s);
 		sync();
 		dense_rank += blk.rr;
