@@ -226,7 +226,7 @@ def main() -> None:
         if agg is None:
             agg = {k: 0.0 for k in ("ms_pivots", "ms_pivots_greedy", "ms_solve", "ms_dense", "ms_dense_gemm", "ms_k_greedy",
                                     "ms_k_panel_solve", "kernel_launches", "greedy_edges", "solve_traffic_model", "gemm_fieldops",
-                                    "solve_rows")}
+                                    "solve_rows", "solve_bytes", "gemm_int8_ops", "nccl_bytes")}
         for k in agg:
             agg[k] += float(getattr(s, k))
     barrier()
@@ -266,19 +266,27 @@ def main() -> None:
         value = ms_per_step / 1e3
         pk = peaks()
         per = {k: v / K for k, v in agg.items()}
-        kernels = {"greedy_pivot_search": per["ms_k_greedy"], "panel_solve": per["ms_k_panel_solve"], "dense_echelon": per["ms_dense"]}
-        dominant = max(kernels, key=kernels.get)
-        if dominant == "greedy_pivot_search":
-            bytes_alg = 4.0 * per["greedy_edges"]        # 4 B per pivot-row entry traversed (device-counted)
-            note = "4 B x pivot-row entries traversed by the BFS (counted on the device)"
-        elif dominant == "panel_solve":
-            bytes_alg = per["solve_traffic_model"]
-            note = "4 B x R x (dependencies + 2 x scheduled columns): panel vectors the pull-form solve must move"
-        else:
-            bytes_alg = 0.0
-            note = "dense echelon (CUDA-core panels + trailing updates): see dense_modp_tops"
-        dur_s = kernels[dominant] / 1e3
-        achieved = bytes_alg / dur_s / 1e9 if dur_s > 0 else 0.0
+        # per-kernel roofline table: algorithmic bytes / live CUDA-event time of that kernel in a step
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)          # dram bytes per step of each kernel, from the committed `ncu --set full` captures
+        table = {
+            "greedy_pivot_search": {"ms": per["ms_k_greedy"], "bytes": 4.0 * per["greedy_edges"],
+                                    "note": "4 B x pivot-row entries traversed by the BFS (counted on the device)"},
+            "panel_solve": {"ms": per["ms_k_panel_solve"], "bytes": per["solve_bytes"],
+                            "note": "per solved row: 8 B x entries of the pivotal rows it reaches + 4 B x dense output columns (SURVEY 8d)"},
+        }
+        for k, v in table.items():
+            v["GBps"] = v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0
+            v["frac"] = v["GBps"] / pk["hbm_gbs"]
+            v["traffic"] = traffic.get(k)
+        dominant = max(table, key=lambda k: table[k]["ms"])
+        d = table[dominant]
+        kernels = {k: v["ms"] for k, v in table.items()}
+        kernels["dense_echelon"] = per["ms_dense"]
+        bytes_alg, note, achieved = d["bytes"], d["note"], d["GBps"]
         line = {
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
@@ -291,12 +299,15 @@ def main() -> None:
             "gpu_launches": int(round(per["kernel_launches"])) * K,
             "clocks": sampler.summary(),
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "bytes_per_launch": bytes_alg,
+                         "frac": achieved / pk["hbm_gbs"], "traffic": d["traffic"], "peak_source": pk["source"], "bytes_per_launch": bytes_alg,
                          "ms_per_launch": kernels[dominant], "note": note},
+            "kernels": {k: {"ms_per_step": round(v["ms"], 3), "algorithmic_GBps": round(v["GBps"], 2), "frac_of_hbm_peak": round(v["frac"], 5),
+                            "traffic": v["traffic"]} for k, v in table.items()},
             "phases_ms": {k: round(per[k], 3) for k in ("ms_pivots", "ms_pivots_greedy", "ms_k_greedy", "ms_solve", "ms_k_panel_solve",
                                                         "ms_dense", "ms_dense_gemm")},
             "schur_rows_per_s": per["solve_rows"] / (per["ms_solve"] / 1e3) if per["ms_solve"] > 0 else None,
             "dense_modp_tops": per["gemm_fieldops"] / (per["ms_dense"] / 1e3) / 1e12 if per["ms_dense"] > 0 else None,
+            "dense_int8_tensor_ops_per_step": per["gemm_int8_ops"], "nccl_bytes_per_step": per["nccl_bytes"],
             "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:

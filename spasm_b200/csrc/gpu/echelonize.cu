@@ -177,8 +177,8 @@ double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R)
 	return ((double) nnz) / (E.m - E.U.n) / R;
 }
 
-/* reference: src/spasm_schur.c:61-193.  Rows come out in p order (the reference with one thread);
- * entries of a row by increasing column. */
+/* reference: src/spasm_schur.c:61-193.  Rows come out in p order (the reference with one thread) and the entries of
+ * a row in the order of the reference's reach pattern (panel.cu: k_schur_emit_dfs). */
 void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
 {
 	cudaStream_t s = ctx().stream;
@@ -193,7 +193,10 @@ void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
 		E.solve_rows(A, d_rows.ptr, R, false);
 		Piece pc;
 		pc.rows = R;
-		panel_to_csr(E.panel, E.Uqinv.ptr, nullptr, 0, nullptr, pc.p, pc.j, pc.x, pc.nnz);
+		/* count, then emit every row in the order of the reference's DFS pattern (it feeds the next pivot round) */
+		panel_to_csr(E.panel, E.Uqinv.ptr, nullptr, 0, nullptr, pc.p, pc.j, pc.x, pc.nnz, true);
+		if (pc.nnz > 0)
+			panel_emit_reference_order(E.panel, A, d_rows.ptr, E.U, E.Uqinv.ptr, E.G.nlevels, pc.p.ptr, pc.j.ptr, pc.x.ptr);
 		total += pc.nnz;
 		pieces.push_back(std::move(pc));
 	}

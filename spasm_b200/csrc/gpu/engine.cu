@@ -58,6 +58,7 @@ void Engine::solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_fir
 	panel_scatter_rows(B, d_rows, R, panel, F, skip_first);
 	panel_solve(G, panel.X, panel.ld, R, F);
 	stats().pub.ms_solve += t.stop_ms();
+	account_bytes(R);
 }
 
 void Engine::solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w)
@@ -70,6 +71,7 @@ void Engine::solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef,
 	panel_scatter_combos(A, d_rows, d_coef, N, w, panel, F);
 	panel_solve(G, panel.X, panel.ld, N, F);
 	stats().pub.ms_solve += t.stop_ms();
+	account_bytes(N);
 }
 
 void Engine::block_from_rows(const DevCsr &B, const int *d_rows, int R, DevBuf<i32> &out, int &ldB)
@@ -100,6 +102,17 @@ void Engine::block_from_combos(const DevCsr &A, const int *d_rows, const i32 *d_
 		gather_q0(out.ptr + (size_t) at * ldB, ldB);
 	}
 	comm_allgather_rows(out.ptr, chunk, ldB);
+}
+
+/* instrumentation (outside the timed solve): algorithmic bytes of the batch, SURVEY 8d accounting */
+void Engine::account_bytes(int R)
+{
+	static const bool off = getenv("SPASM_B200_NO_BYTE_COUNT") != NULL;
+	if (off || U.n == 0)
+		return;
+	/* reached pivot rows (8 B per entry) + the dense output row (4 B per non-pivotal column); the right-hand sides
+	 * themselves (8 B per entry) are small and left out */
+	stats().pub.solve_bytes += panel_reached_bytes(panel, Uqinv.ptr, U.p.ptr) + 4.0 * (double) (m - U.n) * R;
 }
 
 void Engine::gather_q0(i32 *S, int ldS)

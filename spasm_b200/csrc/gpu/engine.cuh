@@ -53,6 +53,7 @@ struct Engine {
 	 * pivots; with several ranks each one solves a slice and the slices are all-gathered */
 	void block_from_rows(const DevCsr &B, const int *d_rows, int R, DevBuf<i32> &out, int &ldB);
 	void block_from_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, DevBuf<i32> &out, int &ldB);
+	void account_bytes(int R);
 	/* gather the q0 columns of the panel into a dense row-major block (R x Sm0, ld = ldS) */
 	void gather_q0(i32 *S, int ldS);
 	/* reduce a dense block by the dense rows found so far, echelonize it, keep its pivot rows. Returns rr. */

@@ -213,7 +213,7 @@ i64 panel_count_nonzero(const Panel &P, const int *d_flag)
 }
 
 void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32 first_val, const int *d_node_to_col,
-                  DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, i64 &nnz)
+                  DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, i64 &nnz, bool count_only)
 {
 	cudaStream_t s = ctx().stream;
 	int R = P.R;
@@ -240,7 +240,7 @@ void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32
 	nnz = fetch(Sp.ptr + R);
 	Sj.alloc((size_t) std::max<i64>(nnz, 1));
 	Sx.alloc((size_t) std::max<i64>(nnz, 1));
-	if (nnz > 0) {
+	if (nnz > 0 && !count_only) {
 		k_panel_sparse<true><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, Sp.ptr, d_node_to_col, Sj.ptr, Sx.ptr, has_first);
 		LAUNCHED(1);
 		if (has_first) {
@@ -248,6 +248,136 @@ void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32
 			LAUNCHED(1);
 		}
 	}
+	KERNEL_CHECK();
+}
+
+}  // namespace sb
+
+namespace sb {
+
+/* Algorithmic bytes of the solved batch in the reference's per-row accounting:
+ * 8 bytes per entry of every pivotal row of U that a right-hand side reaches.  A pivot is counted as reached when its
+ * elimination coefficient X[pivot column][r] is non-zero (the structural reach can only be larger). */
+__global__ void k_reached_bytes(int m, int R, const i32 *__restrict__ X, int ld, const int *__restrict__ qinv,
+                                const i64 *__restrict__ Up, unsigned long long *total)
+{
+	unsigned long long acc = 0;
+	for (int c = blockIdx.x; c < m; c += gridDim.x) {
+		int row = qinv[c];
+		if (row < 0)
+			continue;
+		unsigned long long w = (unsigned long long) (Up[row + 1] - Up[row]);
+		int cnt = 0;
+		for (int r = threadIdx.x; r < R; r += blockDim.x)
+			cnt += X[(size_t) c * ld + r] != 0;
+		acc += w * (unsigned long long) cnt;
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		acc += __shfl_down_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc)
+		atomicAdd(total, 8ull * acc);
+}
+
+double panel_reached_bytes(const Panel &P, const int *d_qinv, const i64 *d_Up)
+{
+	if (P.R == 0 || P.nnodes == 0)
+		return 0;
+	DevBuf<unsigned long long> total(1);
+	total.zero(ctx().stream);
+	k_reached_bytes<<<std::min(P.nnodes, 148 * 16), 128, 0, ctx().stream>>>(P.nnodes, P.R, P.X, P.ld, d_qinv, d_Up, total.ptr);
+	LAUNCHED(1);
+	return (double) fetch(total.ptr);
+}
+
+}  // namespace sb
+
+namespace sb {
+
+/*
+ * Entries of the sparse Schur rows in the REFERENCE's order.  The reference stores a row of S in the order of the
+ * pattern xj[top:m] produced by its depth-first reach (src/spasm_reach.c:21-135, src/spasm_schur.c:156-171), and that
+ * order decides which entry the next pivot round sees first (src/spasm_pivots.c:104-116, :233-237).  A non-pivotal
+ * column is a leaf of the DFS and is finished the moment it is first visited, and xj is filled from the end, so the
+ * kept entries of a row are its non-zero leaves in REVERSE order of first visit.  One thread replays the DFS of one
+ * row (same traversal: start columns in row order, row entries in CSR order) with a private mark bitmap and an
+ * explicit stack whose depth is bounded by the depth of the pivot DAG; the values come from the solved panel.
+ */
+__global__ void k_schur_emit_dfs(int R, const int *__restrict__ rows, const i64 *__restrict__ Bp, const int *__restrict__ Bj,
+                                 const i64 *__restrict__ Up, const int *__restrict__ Uj, const int *__restrict__ qinv,
+                                 const i32 *__restrict__ X, int ld, const i64 *__restrict__ Sp, int *Sj, i32 *Sx,
+                                 int words, unsigned *marks_pool, int *stack_pool, int maxdepth)
+{
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const int nslots = gridDim.x * blockDim.x;
+	unsigned *mark = marks_pool + (size_t) slot * words;
+	int *st_col = stack_pool + (size_t) slot * 2 * maxdepth;
+	int *st_next = st_col + maxdepth;
+	for (int r = slot; r < R; r += nslots) {
+		for (int w = 0; w < words; w++)
+			mark[w] = 0;
+		i64 pos = Sp[r + 1] - 1;                     /* filled from the end, like xj */
+		const int brow = rows[r];
+		for (i64 e = Bp[brow]; e < Bp[brow + 1]; e++) {
+			const int jstart = Bj[e];
+			if (mark[jstart >> 5] & (1u << (jstart & 31)))
+				continue;
+			int head = 0;
+			st_col[0] = jstart;
+			while (head >= 0) {
+				const int j = st_col[head];
+				const int i = qinv[j];
+				if (!(mark[j >> 5] & (1u << (j & 31)))) {
+					mark[j >> 5] |= 1u << (j & 31);
+					st_next[head] = 0;
+				}
+				if (i < 0) {
+					const i32 v = X[(size_t) j * ld + r];
+					if (v != 0) {
+						Sj[pos] = j;
+						Sx[pos] = v;
+						pos--;
+					}
+					head--;
+					continue;
+				}
+				const i64 base = Up[i];
+				const int len = (int) (Up[i + 1] - base);
+				bool pushed = false;
+				for (int k = st_next[head]; k < len; k++) {
+					const int c = Uj[base + k];
+					if (mark[c >> 5] & (1u << (c & 31)))
+						continue;
+					st_next[head] = k + 1;
+					if (head + 1 < maxdepth) {
+						head++;
+						st_col[head] = c;
+						pushed = true;
+					}
+					break;
+				}
+				if (!pushed)
+					head--;
+			}
+		}
+	}
+}
+
+void panel_emit_reference_order(const Panel &P, const DevCsr &B, const int *d_rows, const DevCsr &U, const int *d_qinv,
+                                int dag_depth, const i64 *d_Sp, int *d_Sj, i32 *d_Sx)
+{
+	if (P.R == 0)
+		return;
+	cudaStream_t s = ctx().stream;
+	int words = (P.nnodes + 31) / 32;
+	int maxdepth = dag_depth + 8;
+	int threads = 64;
+	int blocks = std::min<int>(cdiv(P.R, threads), 148 * 8);
+	size_t nslots = (size_t) blocks * threads;
+	DevBuf<unsigned> marks(nslots * words);
+	DevBuf<int> stacks(nslots * 2 * maxdepth);
+	k_schur_emit_dfs<<<blocks, threads, 0, s>>>(P.R, d_rows, B.p, B.j, U.p, U.j, d_qinv, P.X, P.ld, d_Sp, d_Sj, d_Sx, words, marks.ptr,
+	                                           stacks.ptr, maxdepth);
+	LAUNCHED(1);
 	KERNEL_CHECK();
 }
 

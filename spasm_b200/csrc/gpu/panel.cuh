@@ -34,6 +34,13 @@ i64 panel_count_nonzero(const Panel &P, const int *d_flag);
 /* CSR of the panel restricted to nodes with flag[node] < 0, entries of a row by increasing node.
  * If d_first != NULL, row r starts with the extra entry (first_col[r], first_val) (used by rref / kernel). */
 void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32 first_val, const int *d_node_to_col,
-                  DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, i64 &nnz);
+                  DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, i64 &nnz, bool count_only = false);
+
+/* fill Sj/Sx of rows counted by panel_to_csr(count_only) with the entries in the reference's DFS pattern order */
+void panel_emit_reference_order(const Panel &P, const DevCsr &B, const int *d_rows, const DevCsr &U, const int *d_qinv,
+                                int dag_depth, const i64 *d_Sp, int *d_Sj, i32 *d_Sx);
+
+/* 8 * sum over right-hand sides of nnz(U rows reached): the dominant term of SURVEY 8d's algorithmic bytes */
+double panel_reached_bytes(const Panel &P, const int *d_qinv, const i64 *d_Up);
 
 }  // namespace sb

@@ -1,15 +1,21 @@
 #!/bin/bash
-# Profiling recipe of this repository (B200_PROFILING.md): launch list of one steady-state bench step + full captures
-# of the two dominant kernels.  Outputs land in gpurun_out/ (copy summaries to profiles/).
+# Profiling recipe of this repository (B200_PROFILING.md), run on a B200 through gpurun:
+#   1. launch list (gpu__time_duration) of one steady-state step of the bench workload (config 2) and of config 1
+#   2. `ncu --set full` captures of the dominant kernels
+# Outputs land in gpurun_out/ (scratch); tools/summarize_profiles.py turns them into profiles/*.md.
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-# 1. every launch of one steady-state step with its device time (3 warm-up steps = ~1800 launches are skipped)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-1776} -c ${COUNT:-700} --csv --log-file gpurun_out/launches.csv \
+LPS=${LPS:-382}     # launches per echelonize step of config 2 (bench prints gpu_launches / steps)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * LPS)) -c $LPS --csv --log-file gpurun_out/launches_config2.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-# 2. the two dominant kernels, once each, full metric set
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_greedy -s 3 -c 1 -f -o gpurun_out/prof_greedy \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_greedy.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_panel_solve -s 13 -c 1 -f -o gpurun_out/prof_solve \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_solve.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * 1189)) -c 1189 --csv --log-file gpurun_out/launches_config1.csv \
+    python bench.py --workload config1 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench1_under_ncu.log 2>&1
+for k in k_greedy_ooo k_panel_solve_flow k_kahn_async k_rref_panel; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_$k \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_$k.log 2>&1
+done
+# the tensor-core product: config 1 has the 1000 x 1000 x 6813 block reductions
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_umma_gemm_sub -s 20 -c 1 -f -o gpurun_out/prof_k_umma_gemm_sub \
+    python bench.py --workload config1 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_umma.log 2>&1
 ls -la gpurun_out/
