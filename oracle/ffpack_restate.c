@@ -102,6 +102,16 @@ static void store(void *A, size_t k, oracle_datatype t, i64 v)
  * the pivot columns (increasing); rows r..n-1 are zero.  Returns r.
  */
 #define PANEL 48
+
+/* acc[j] += w * src[j] with 32 x 32 -> 64-bit products (vpmuldq when AVX2 is there; the clone is chosen at load time,
+ * so the library built in the container also runs on the GPU box's host) */
+__attribute__((target_clones("avx2", "default")))
+static void axpy_widening(i64 *restrict acc, i32 w, const i32 *restrict src, int width)
+{
+	for (int j = 0; j < width; j++)
+		acc[j] += (i64) w * (i64) src[j];
+}
+
 int oracle_dense_rref_i32(i64 p, int n, int m, i32 *W, int *pivcol)
 {
 	int r = 0;
@@ -188,13 +198,23 @@ int oracle_dense_rref_i32(i64 p, int n, int m, i32 *W, int *pivcol)
 		int width = m - c0;
 		for (int s = 0; s < k; s++)
 			memcpy(oldrows + (size_t) s * width, W + (size_t) prow[s] * m + c0, width * sizeof(i32));
-		for (int i = 0; i < n; i++)
+		#pragma omp parallel for schedule(static)
+		for (int i = 0; i < n; i++) {
+			i64 piv_vals[PANEL];
+			for (int s = 0; s < k; s++)
+				piv_vals[s] = W[(size_t) i * m + c0 + pcol[s]];
 			for (int t = 0; t < k; t++) {
 				i64 acc = 0;
-				for (int s = 0; s < k; s++)
-					acc = bal(acc + bal((i64) W[(size_t) i * m + c0 + pcol[s]] * Minv[s * PANEL + t], p), p);
-				Wmul[(size_t) i * PANEL + t] = (i32) acc;
+				if (fast) {                   /* 48 products below 2^50 fit an i64 */
+					for (int s = 0; s < k; s++)
+						acc += piv_vals[s] * Minv[s * PANEL + t];
+				} else {
+					for (int s = 0; s < k; s++)
+						acc = (acc + (piv_vals[s] * Minv[s * PANEL + t]) % p) % p;
+				}
+				Wmul[(size_t) i * PANEL + t] = (i32) bal(acc, p);
 			}
+		}
 		for (int s = 0; s < k; s++)
 			for (int t = 0; t < k; t++)
 				Wmul[(size_t) prow[s] * PANEL + t] = (i32) bal((s == t) - Minv[s * PANEL + t], p);
@@ -215,12 +235,9 @@ int oracle_dense_rref_i32(i64 p, int n, int m, i32 *W, int *pivcol)
 					for (int j = 0; j < width; j++)
 						acc[j] = 0;
 					for (int t = 0; t < k; t++) {
-						i64 w = mul[t];
-						if (w == 0)
+						if (mul[t] == 0)
 							continue;
-						const i32 *src = oldrows + (size_t) t * width;
-						for (int j = 0; j < width; j++)
-							acc[j] += w * (i64) src[j];
+						axpy_widening(acc, mul[t], oldrows + (size_t) t * width, width);
 					}
 					for (int j = 0; j < width; j++)
 						row[j] = (i32) bal((i64) row[j] - acc[j], p);
