@@ -465,19 +465,44 @@ k_panel_solve(const i64 *__restrict__ ptr, const int *__restrict__ src, const i3
  * poll.  Sources (level-0 columns) are final from the start and are never scheduled.  The values do not depend
  * on the schedule (each column is still written once, from final columns).
  */
-__global__ void __launch_bounds__(256)
+#define FLOW_MAXD 8      /* dependents of a column whose metadata is prefetched */
+#define FLOW_MAXE 8      /* dependencies per column kept in shared memory */
+
+struct FlowMeta {
+	int node;
+	int cnt;             /* number of dependencies (may exceed FLOW_MAXE: the rest is read from global memory) */
+	i64 e0;
+	int src[FLOW_MAXE];
+	i32 val[FLOW_MAXE];
+};
+
+__global__ void __launch_bounds__(1024)
 k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                    const i64 *__restrict__ rptr, const int *__restrict__ rdst, const int *__restrict__ level,
                    int *pending, int *queue, int nseeds, int nscheduled, int *tail, int *ticket, int *done, int *error,
                    int4 *X, int ld4, int R4, Zp F)
 {
+	/* The critical path of a pass is a chain of the DAG walked by one CTA.  To keep a hop short, the metadata of the
+	 * columns that depend on the current one (their dependency lists) is prefetched into shared memory while the
+	 * current column is being computed: when one of them is released and becomes the next job, only the panel
+	 * vectors themselves remain to be loaded. */
 	__shared__ int s_node, s_next;
+	__shared__ FlowMeta cur, dep[FLOW_MAXD];
 	const int tid = threadIdx.x;
-	int next = -1;
+	int next_slot = -1;          /* >= 0: next job is dep[next_slot] */
 	for (;;) {
-		int c = next;
-		next = -1;
-		if (c < 0) {
+		/* ---- 1. the job and its metadata */
+		if (next_slot >= 0) {
+			if (tid < FLOW_MAXE) {
+				cur.src[tid] = dep[next_slot].src[tid];
+				cur.val[tid] = dep[next_slot].val[tid];
+			}
+			if (tid == 0) {
+				cur.node = dep[next_slot].node;
+				cur.cnt = dep[next_slot].cnt;
+				cur.e0 = dep[next_slot].e0;
+			}
+		} else {
 			if (tid == 0) {
 				const int t = atomicAdd(ticket, 1);
 				int got = -2;
@@ -501,22 +526,55 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 				s_node = got;
 			}
 			__syncthreads();
-			c = s_node;
-			__syncthreads();
-			if (c < 0)
+			const int c0 = s_node;
+			if (c0 < 0)
 				return;
+			const i64 e0 = ptr[c0];
+			const int cnt = (int) (ptr[c0 + 1] - e0);
+			if (tid < FLOW_MAXE && tid < cnt) {
+				cur.src[tid] = src[e0 + tid];
+				cur.val[tid] = val[e0 + tid];
+			}
+			if (tid == 0) {
+				cur.node = c0;
+				cur.cnt = cnt;
+				cur.e0 = e0;
+			}
 		}
-		/* the column, for all right-hand sides; dependencies are read around L1 (they were written by other SMs) */
+		__syncthreads();
+		const int c = cur.node;
+		const i64 rb = rptr[c], re = rptr[c + 1];
+		/* ---- 2. prefetch the metadata of the dependents (overlaps with the loads of the column below) */
+		if (tid < FLOW_MAXD * FLOW_MAXE) {
+			const int di = tid / FLOW_MAXE, ei = tid % FLOW_MAXE;
+			if (rb + di < re) {
+				const int d = rdst[rb + di];
+				const i64 de0 = ptr[d];
+				const int dcnt = (int) (ptr[d + 1] - de0);
+				if (ei < dcnt) {
+					dep[di].src[ei] = src[de0 + ei];
+					dep[di].val[ei] = val[de0 + ei];
+				}
+				if (ei == 0) {
+					dep[di].node = d;
+					dep[di].cnt = dcnt;
+					dep[di].e0 = de0;
+				}
+			}
+		}
+		/* ---- 3. the column, for all right-hand sides; dependencies are read around L1 (written by other SMs) */
 		{
-			const i64 e0 = ptr[c], e1 = ptr[c + 1];
+			const int cnt = cur.cnt, cached = min(cnt, FLOW_MAXE);
+			const i64 e0 = cur.e0;
 			int4 *Xc = X + (size_t) c * ld4;
 			for (int r = tid; r < R4; r += blockDim.x) {
 				int4 b = Xc[r];
 				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
 				int pendingred = 0;
-				for (i64 e = e0; e < e1; e++) {
-					const i64 v = val[e];
-					const int4 xs = __ldcg(&X[(size_t) src[e] * ld4 + r]);
+				for (int e = 0; e < cnt; e++) {
+					const i64 v = (e < cached) ? cur.val[e] : val[e0 + e];
+					const int sc = (e < cached) ? cur.src[e] : src[e0 + e];
+					const int4 xs = __ldcg(&X[(size_t) sc * ld4 + r]);
 					a0 -= v * xs.x;
 					a1 -= v * xs.y;
 					a2 -= v * xs.z;
@@ -534,12 +592,12 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 		if (tid == 0)
 			s_next = -1;
 		__syncthreads();
-		/* release the dependents */
-		const i64 b = rptr[c], e = rptr[c + 1];
-		for (i64 k = b + tid; k < e; k += blockDim.x) {
-			const int d = rdst[k];
+		/* ---- 4. release the dependents; keep one of the prefetched ones as the next job */
+		for (i64 k = rb + tid; k < re; k += blockDim.x) {
+			const int di = (int) (k - rb);
+			const int d = (di < FLOW_MAXD) ? dep[di].node : rdst[k];
 			if (atomicSub(&pending[d], 1) == 1) {
-				if (atomicCAS(&s_next, -1, d) != -1) {
+				if (di >= FLOW_MAXD || atomicCAS(&s_next, -1, di) != -1) {
 					const int pos = atomicAdd(tail, 1);
 					__threadfence();
 					*((volatile int *) &queue[pos]) = d;
@@ -547,7 +605,7 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 			}
 		}
 		__syncthreads();
-		next = s_next;
+		next_slot = s_next;
 		if (tid == 0)
 			atomicAdd(done, 1);
 		__syncthreads();
@@ -571,12 +629,14 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		CUDA_CHECK(cudaMemcpyAsync(queue.ptr, G.seeds.ptr, (size_t) G.nseeds * sizeof(int), cudaMemcpyDeviceToDevice, s));
 		int h_init[4] = {G.nseeds, 0, 0, 0};      /* tail, ticket, done, error */
 		CUDA_CHECK(cudaMemcpyAsync(counters.ptr, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
+		/* one pass over the right-hand sides per column when possible: the column is the unit of the critical path */
+		int threads = getenv("SPASM_B200_FLOW_THREADS") ? atoi(getenv("SPASM_B200_FLOW_THREADS")) : (R4 > 512 ? 1024 : R4 > 256 ? 512 : 256);
 		int occ = 0;
-		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, 256, 0));
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, threads, 0));
 		int blocks = std::max(1, std::min(occ, 8)) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
 		GpuTimer tk;
 		tk.start();
-		k_panel_solve_flow<<<blocks, 256, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, G.level.ptr, pending.ptr, queue.ptr,
+		k_panel_solve_flow<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, G.level.ptr, pending.ptr, queue.ptr,
 		                                         G.nseeds, G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3,
 		                                         (int4 *) X, ld4, R4, F);
 		LAUNCHED(1);
