@@ -70,6 +70,9 @@ void spasm_b200_prng_stream(int64_t prime, uint64_t seed, uint32_t seq, int coun
 /* test hook: C (M x N) -= A (M x K) * B (K x N) mod prime on host row-major matrices, through the CUDA-core product
  * (use_tensor = 0) or the tcgen05 int8 limb-split product (use_tensor = 1) */
 void spasm_b200_gemm_sub(int64_t prime, int M, int N, int K, int32_t *C, const int32_t *A, const int32_t *B, int use_tensor);
+/* average ms of one C -= A*B on device-resident pseudo-random operands; mode 0 = CUDA cores, 1 = tensor cores (operands
+ * split into int8 limb planes inside the timed region), 2 = B planes prepared beforehand, 3 = tensor kernel alone */
+double spasm_b200_gemm_time(int64_t prime, int M, int N, int K, int mode, int reps);
 
 /* Multi-GPU (one process per GPU).  Rank 0 creates a 128-byte NCCL unique id, the caller distributes it (e.g.
  * torch.distributed.broadcast), every rank calls spasm_b200_comm_init.  From then on spasm_echelonize shards the

@@ -28,7 +28,7 @@ GCC = "/usr/bin/gcc"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-                     "-ccbin", "/usr/bin/g++", f"-I{INCLUDE}", f"-I{GPU_DIR}"]
+                     "-ccbin", "/usr/bin/g++", f"-I{INCLUDE}", f"-I{GPU_DIR}"] + os.environ.get("SPASM_B200_NVCC_EXTRA", "").split()
 GCC_FLAGS = ["-std=gnu11", "-O2", "-g", "-fPIC", "-Wall", "-Wextra", "-Wno-format-truncation", f"-I{INCLUDE}"]
 
 

@@ -22,6 +22,11 @@ void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ld
 /* the same product on the int8 tensor cores (umma_gemm.cu): tcgen05.mma kind::i8 on signed byte limbs */
 bool umma_gemm_available(const Zp &F);
 void umma_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F);
+/* operands pre-split into int8 limb planes, tile-packed in the UMMA shared-memory layout (umma_gemm.cu, version 2) */
+size_t umma_packed_bytes(int rows, int K, int L);
+int umma_limbs(const Zp &F);
+void umma_pack(const i32 *src, int ld, int rows, int K, bool rowmajor_k, int8_t *dst, const Zp &F);
+void umma_gemm_sub_packed(i32 *C, int ldc, const int8_t *Ap, const int8_t *Bp, int M, int N, int K, const Zp &F);
 
 struct RrefResult {
 	int rank = 0;

@@ -131,12 +131,21 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 	 *   B <- B - B[:, P_b] * D_b        D_b = [ I on P_b | ... ] */
 	double gemm_ms = 0;
 	DevBuf<i32> Ac;
+	DevBuf<int8_t> Apack;
 	for (DenseBlock &blk : blocks) {
-		const int lda = (blk.rr + 3) & ~3;      /* 16-byte aligned rows for the vector loads of the tensor-core staging */
+		const int lda = (blk.rr + 3) & ~3;
 		Ac.ensure((size_t) rows * lda);
 		tg.start();
 		dense_gather_columns(B, ldB, rows, blk.d_pivcol.ptr, blk.rr, Ac.ptr, lda);
-		dense_gemm_sub(B, ldB, Ac.ptr, lda, blk.D.ptr, blk.ld, rows, Sm0, blk.rr, F);
+		if (blk.Dpack.ptr && (double) rows * Sm0 * blk.rr >= 4e6) {
+			/* tensor cores: the block's rows were split into limb planes when it was created */
+			Apack.ensure(umma_packed_bytes(rows, blk.rr, umma_limbs(F)));
+			umma_pack(Ac.ptr, lda, rows, blk.rr, true, Apack.ptr, F);
+			umma_gemm_sub_packed(B, ldB, Apack.ptr, blk.Dpack.ptr, rows, Sm0, blk.rr, F);
+			stats().pub.gemm_fieldops += 2.0 * rows * (double) Sm0 * blk.rr;
+		} else {
+			dense_gemm_sub(B, ldB, Ac.ptr, lda, blk.D.ptr, blk.ld, rows, Sm0, blk.rr, F);
+		}
 		gemm_ms += tg.stop_ms();
 	}
 	/* Echelonize on the columns that are not pivotal yet only: after the reduction the block is zero on the pivot
@@ -187,6 +196,10 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 		for (int cpiv : blk.pivcol)
 			own[cpiv] = 1;
 		blk.d_own.upload(own.data(), own.size(), s);
+		if (blk.rr >= 64 && umma_gemm_available(F)) {
+			blk.Dpack.alloc(umma_packed_bytes(Sm0, blk.rr, umma_limbs(F)));
+			umma_pack(blk.D.ptr, blk.ld, Sm0, blk.rr, false, blk.Dpack.ptr, F);
+		}
 		sync();
 		dense_rank += blk.rr;
 		blocks.push_back(std::move(blk));

@@ -21,6 +21,7 @@ struct DenseBlock {
 	std::vector<int> pivcol;         /* pivot column (index into q0) of each row, increasing */
 	DevBuf<int> d_pivcol;
 	DevBuf<unsigned char> d_own;     /* flag per q0 column: pivot of this block */
+	DevBuf<int8_t> Dpack;            /* D split into int8 limb planes, tile-packed for the tensor cores (umma_gemm.cu); may be empty */
 };
 
 struct Engine {
