@@ -43,6 +43,14 @@ Context &ctx();            /* lazily initialised; aborts when no usable sm_100 d
 struct Stats;
 Stats &stats();
 
+/* -------------------------------------------------------------------- large results to pageable host memory
+ * A cudaMemcpy into freshly malloc'ed memory runs at the speed of the page faults it triggers (about 2 GB/s), which
+ * made the download of a 2.4 GB echelon form cost more than its computation.  download_bulk asks for huge pages on
+ * the destination, copies chunk by chunk into pinned staging buffers and lets several host threads move each chunk
+ * to its place (they take the page faults in parallel) while the next chunk is in flight. */
+static const size_t BULK_DOWNLOAD_BYTES = (size_t) 16 << 20;
+void download_bulk(void *host, const void *dev, size_t bytes);
+
 /* -------------------------------------------------------------------- device buffers */
 template <typename T> struct DevBuf {
 	T *ptr = nullptr;
@@ -83,8 +91,12 @@ template <typename T> struct DevBuf {
 		ensure(n);
 		if (n) CUDA_CHECK(cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
 	}
+	/* small transfers are asynchronous on s; large ones take the staged path (download_bulk) and are complete on return */
 	void download(T *host, size_t n, cudaStream_t s) const {
-		if (n) CUDA_CHECK(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+		if (n * sizeof(T) >= BULK_DOWNLOAD_BYTES)
+			download_bulk(host, ptr, n * sizeof(T));
+		else if (n)
+			CUDA_CHECK(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, s));
 	}
 	operator T *() const { return ptr; }
 };

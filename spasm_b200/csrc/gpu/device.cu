@@ -3,6 +3,9 @@
  */
 #include "common.cuh"
 #include "stats.cuh"
+#include <sys/mman.h>
+#include <thread>
+#include <unistd.h>
 
 namespace sb {
 
@@ -47,6 +50,71 @@ Context &ctx()
 	unsigned long long keep = ~0ull;
 	CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 	return g_ctx;
+}
+
+/* memcpy by several threads: the destination is usually untouched memory, so this is where the page faults happen */
+static void parallel_memcpy(char *dst, const char *src, size_t bytes, int nthreads)
+{
+	if (nthreads <= 1 || bytes < ((size_t) 1 << 20)) {
+		memcpy(dst, src, bytes);
+		return;
+	}
+	std::vector<std::thread> pool;
+	size_t slice = ((bytes / nthreads) + 4095) & ~(size_t) 4095;
+	for (int t = 1; t < nthreads; t++) {
+		size_t lo = std::min(bytes, (size_t) t * slice), hi = std::min(bytes, lo + slice);
+		if (hi > lo)
+			pool.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+	}
+	memcpy(dst, src, std::min(bytes, slice));
+	for (std::thread &th : pool)
+		th.join();
+}
+
+void download_bulk(void *host, const void *dev, size_t bytes)
+{
+	if (bytes == 0)
+		return;
+	cudaStream_t s = ctx().stream;
+	constexpr int NB = 3;
+	const size_t CH = (size_t) 32 << 20;
+	static char *pin[NB] = {nullptr, nullptr, nullptr};
+	static cudaEvent_t ev[NB];
+	static int nthreads = 0;
+	if (!pin[0]) {
+		for (int k = 0; k < NB; k++) {
+			CUDA_CHECK(cudaHostAlloc((void **) &pin[k], CH, cudaHostAllocDefault));
+			CUDA_CHECK(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+		}
+		const char *e = getenv("SPASM_B200_COPY_THREADS");
+		long online = sysconf(_SC_NPROCESSORS_ONLN);
+		nthreads = e ? atoi(e) : (int) std::max(1L, std::min(8L, online / 2));
+	}
+#ifdef MADV_HUGEPAGE
+	{
+		/* 2 MB pages where the kernel grants them: 512 times fewer faults (no effect, and no harm, elsewhere) */
+		const uintptr_t two_mb = (uintptr_t) 2 << 20;
+		uintptr_t lo = ((uintptr_t) host + two_mb - 1) & ~(two_mb - 1), hi = ((uintptr_t) host + bytes) & ~(two_mb - 1);
+		if (hi > lo)
+			(void) madvise((void *) lo, hi - lo, MADV_HUGEPAGE);
+	}
+#endif
+	const size_t nchunks = (bytes + CH - 1) / CH;
+	for (size_t i = 0; i < nchunks + NB - 1; i++) {
+		if (i < nchunks) {
+			size_t off = i * CH, len = std::min(CH, bytes - off);
+			CUDA_CHECK(cudaMemcpyAsync(pin[i % NB], (const char *) dev + off, len, cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaEventRecord(ev[i % NB], s));
+		}
+		if (i + 1 >= (size_t) NB) {
+			size_t j = i + 1 - NB;          /* its slot is the one the next iteration refills */
+			if (j < nchunks) {
+				size_t off = j * CH, len = std::min(CH, bytes - off);
+				CUDA_CHECK(cudaEventSynchronize(ev[j % NB]));
+				parallel_memcpy((char *) host + off, pin[j % NB], len, nthreads);
+			}
+		}
+	}
 }
 
 void DevCsr::upload(const struct spasm_csr *A)

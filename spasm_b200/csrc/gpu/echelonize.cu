@@ -538,6 +538,16 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 {
 	cudaStream_t s = ctx().stream;
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace] assemble/%-19s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	struct Piece { DevBuf<i64> p; DevBuf<int> j; DevBuf<i32> x; i64 nnz; int rows; };
 	std::vector<Piece> pieces;
 	i64 total = E.U.nnz;
@@ -548,6 +558,7 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 		total += pc.nnz;
 		pieces.push_back(std::move(pc));
 	}
+	lap("dense rows -> CSR");
 	int rank = E.rank();
 	struct spasm_csr *U = spasm_csr_alloc(std::max(rank, n_rows_alloc), E.m, std::max<i64>(total, 1), E.prime, true);
 	int *qinv = (int *) spasm_malloc((i64) std::max(E.m, 1) * sizeof(int));
@@ -556,6 +567,7 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	E.U.x.download(U->x, (size_t) E.U.nnz, s);
 	E.Uqinv.download(qinv, (size_t) E.m, s);
 	sync();
+	lap("structural rows");
 	i64 off = E.U.nnz;
 	int row = E.U.n;
 	for (size_t b = 0; b < pieces.size(); b++) {
@@ -572,6 +584,7 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 		off += pc.nnz;
 		row += pc.rows;
 	}
+	lap("download dense rows");
 	stats().pub.d2h_bytes += total * 8 + (i64) (rank + 1) * 8 + (i64) E.m * 4;
 	U->n = rank;
 	/* trim like the reference does (echelonize.c:603-604) */
@@ -585,6 +598,7 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	fact->qinv = qinv;
 	fact->p = NULL;
 	fact->Ltmp = NULL;
+	lap("trim");
 	return fact;
 }
 
@@ -729,10 +743,15 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 	ctx();
 	GpuTimer timer;
 	timer.start();
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
 	DevCsr dA0;
 	dA0.upload(A);
 	Engine E;
 	echelonize_core(E, dA0, opts);
+	if (trace) {
+		sb::sync();
+		fprintf(stderr, "[trace] upload + echelonize_core %8.3f ms\n", 1e3 * (spasm_wtime() - start));
+	}
 	struct spasm_lu *fact = assemble(E, 0);
 	stats().pub.ms_device_echelonize = timer.stop_ms();
 	stats().pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);

@@ -536,6 +536,9 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 				sh.np_now = ld_volatile(a.npiv);
 			__syncthreads();
 			const int np_now = sh.np_now, np_old = sh.npiv_local;
+			/* read here, between two barriers: thread 0 resets sh.npend as soon as it enters the collection below,
+			 * and a warp that evaluated the condition after that would skip the block and its barriers */
+			const bool collect_pending = sh.npend < 0;
 			__syncthreads();
 			if (np_now != np_old) {
 				for (int t = np_old + tid; t < np_now; t += T) {
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 				continue;                       /* close the search again */
 			}
 			/* ---- can any unresolved lower row still matter? */
-			if (sh.npend < 0) {                 /* first time: collect the unresolved rows below i */
+			if (collect_pending) {              /* first time: collect the unresolved rows below i */
 				if (tid == 0) {
 					sh.npend = 0;
 					sh.blocked = 0;
@@ -583,7 +586,9 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 							sh.pend[pos] = r;
 					}
 				__syncthreads();
-				if (sh.npend > PEND_CAP) {      /* too many to track: look again later */
+				const bool overflow = sh.npend > PEND_CAP;
+				__syncthreads();                /* every thread has read the count before thread 0 resets it */
+				if (overflow) {                 /* too many to track: look again later */
 					if (tid == 0)
 						sh.npend = -1;
 					__syncthreads();
@@ -790,6 +795,15 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		edges.zero(s);
 		CUDA_CHECK(cudaMemsetAsync(counters.ptr + 3, 0, 5 * sizeof(int), s));
 		static const bool ordered = getenv("SPASM_B200_GREEDY_ORDERED") != NULL;
+		/* development: run the ordered kernel as well, from the same starting point, and report the differences */
+		static const bool shadow = getenv("SPASM_B200_GREEDY_SHADOW") != NULL;
+		DevBuf<int> pinv0, qinv0;
+		if (shadow) {
+			pinv0.alloc((size_t) n);
+			qinv0.alloc((size_t) m);
+			CUDA_CHECK(cudaMemcpyAsync(pinv0.ptr, d_pinv, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+			CUDA_CHECK(cudaMemcpyAsync(qinv0.ptr, d_qinv, (size_t) m * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		}
 		GpuTimer tk;
 		if (ordered || n >= GREEDY_TAG) {
 			a.journal = journal.ptr;
@@ -825,6 +839,9 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			if (occ2 < 1)
 				errx(1, "[spasm-b200] greedy pivot search kernel does not fit");
 			int blocks2 = std::min(blocks, std::min(occ2, per_sm) * ctx().sm_count);
+			/* an unresolved row is held by a CTA, so a row never has more pending lower rows than there are CTAs:
+			 * keep that below the capacity of the pending list (the overflow path stays as a safety net) */
+			blocks2 = std::min(blocks2, PEND_CAP);
 			tk.start();
 			k_greedy_ooo<<<blocks2, threads, smem, s>>>(o);
 			k_strip_tags<<<cdiv(m, 256), 256, 0, s>>>(m, d_qinv);
@@ -833,6 +850,40 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_greedy += tk.stop_ms();
+		if (shadow && !(ordered || n >= GREEDY_TAG)) {
+			int got = fetch(counters.ptr + 4);
+			DevBuf<int> counters2(8), journal2((size_t) n + 1), status2((size_t) n + 1);
+			counters2.zero(s);
+			status2.zero(s);
+			a.qinv = qinv0.ptr;
+			a.pinv = pinv0.ptr;
+			a.journal = journal2.ptr;
+			a.npiv = counters2.ptr + 3;
+			a.found = counters2.ptr + 4;
+			a.ticket = counters2.ptr + 5;
+			a.hint = counters2.ptr + 6;
+			a.status = status2.ptr;
+			a.bitmaps = bitmaps.ptr;
+			a.queues = queues.ptr;
+			a.edges = edges.ptr;
+			k_greedy<<<blocks, threads, smem, s>>>(a);
+			KERNEL_CHECK();
+			std::vector<int> p1((size_t) n), p2((size_t) n);
+			CUDA_CHECK(cudaMemcpyAsync(p1.data(), d_pinv, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, s));
+			CUDA_CHECK(cudaMemcpyAsync(p2.data(), pinv0.ptr, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, s));
+			int want = fetch(counters2.ptr + 4);
+			sync();
+			int ndiff = 0, first = -1;
+			for (int i = 0; i < n; i++)
+				if (p1[i] != p2[i]) {
+					if (first < 0)
+						first = i;
+					ndiff++;
+				}
+			if (ndiff)
+				errx(1, "[spasm-b200] greedy pivot search: the out-of-order kernel (%d pivots) and the ordered kernel (%d pivots) differ on %d rows, "
+				        "first on row %d (column %d vs %d)", got, want, ndiff, first, p1[first], p2[first]);
+		}
 		out.greedy = fetch(counters.ptr + 4);
 		stats().pub.greedy_edges += (i64) fetch(edges.ptr);
 		stats().pub.ms_pivots_greedy += timer.stop_ms();

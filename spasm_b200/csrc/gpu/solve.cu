@@ -360,8 +360,34 @@ void depgraph_schedule(DepGraph &G)
 	CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
 	sync();
 	lap("kahn");
-	if (h[3] != n || h[2] != 0)
-		errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d nodes scheduled): invalid U / qinv", h[3], n);
+	if (h[3] != n || h[2] != 0) {
+		/* say which side is wrong: redo the topological sort on the host */
+		std::vector<i64> hp((size_t) n + 1);
+		std::vector<int> hs((size_t) std::max<i64>(G.ndeps, 1));
+		CUDA_CHECK(cudaMemcpy(hp.data(), G.ptr.ptr, hp.size() * sizeof(i64), cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(hs.data(), G.src.ptr, (size_t) G.ndeps * sizeof(int), cudaMemcpyDeviceToHost));
+		std::vector<int> deg((size_t) n, 0), stack;
+		std::vector<std::vector<int>> out((size_t) n);
+		for (int c = 0; c < n; c++)
+			for (i64 k = hp[c]; k < hp[c + 1]; k++) {
+				deg[c]++;
+				out[hs[k]].push_back(c);
+			}
+		for (int c = 0; c < n; c++)
+			if (deg[c] == 0)
+				stack.push_back(c);
+		int seen = 0;
+		while (!stack.empty()) {
+			int u = stack.back();
+			stack.pop_back();
+			seen++;
+			for (int c : out[u])
+				if (--deg[c] == 0)
+					stack.push_back(c);
+		}
+		errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d nodes scheduled on the device, %d on the host, "
+		        "error flag %d): %s", h[3], n, seen, h[2], seen == n ? "internal error of the device scheduler" : "invalid U / qinv");
+	}
 
 	/* deterministic order inside each level: sort by (level, node); level boundaries by binary search on the keys */
 	DevBuf<unsigned long long> keys((size_t) n), keys2((size_t) n);
