@@ -136,7 +136,7 @@ def run_reference(args) -> None:
         os.dup2(saved, 2)
     v = sum(times) / len(times)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 mod p (balanced)", "data": "synthetic",
             "config": {"workload": f"{args.workload} (scale {args.scale}): {t.n}x{t.m}, {t.nz} entries, p={t.prime}", "rank": rank_found},
             "cpu_baseline": {"value": v, "unit": "s", "cores": cores, "kind": kind,
@@ -289,7 +289,7 @@ def main() -> None:
         bytes_alg, note, achieved = d["bytes"], d["note"], d["GBps"]
         line = {
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 mod p (balanced)", "data": "synthetic",
             "config": {"workload": f"{args.workload} (scale {args.scale}): {t.n}x{t.m}, {t.nz} entries, p={t.prime}",
                        "rank": int(rk), "l2": "flushed between timed steps (512 MB write)",

@@ -43,45 +43,50 @@ static struct spasm_csr *csr_to_host(const DevCsr &S)
 }
 
 /* concatenate per-batch CSR pieces (device) into one host CSR */
+/* a batch of result rows, kept in HBM until the whole result is known: the host matrix is then allocated once and
+ * every batch is downloaded straight to its place (no intermediate host copy: a 3 GB result used to be touched
+ * three times by one host thread) */
 struct HostPiece {
-	std::vector<i64> p;
-	std::vector<int> j;
-	std::vector<i32> x;
+	DevBuf<i64> p;
+	DevBuf<int> j;
+	DevBuf<i32> x;
+	int rows = 0;
+	i64 nnz = 0;
 };
 
-static void piece_download(const DevBuf<i64> &Sp, const DevBuf<int> &Sj, const DevBuf<i32> &Sx, int rows, i64 nnz, HostPiece &out)
+static void piece_download(DevBuf<i64> &Sp, DevBuf<int> &Sj, DevBuf<i32> &Sx, int rows, i64 nnz, HostPiece &out)
 {
-	cudaStream_t s = ctx().stream;
-	out.p.resize((size_t) rows + 1);
-	out.j.resize((size_t) nnz);
-	out.x.resize((size_t) nnz);
-	Sp.download(out.p.data(), (size_t) rows + 1, s);
-	Sj.download(out.j.data(), (size_t) nnz, s);
-	Sx.download(out.x.data(), (size_t) nnz, s);
-	sync();
-	stats().pub.d2h_bytes += nnz * 8 + (i64) (rows + 1) * 8;
+	out.p = std::move(Sp);
+	out.j = std::move(Sj);
+	out.x = std::move(Sx);
+	out.rows = rows;
+	out.nnz = nnz;
 }
 
 static struct spasm_csr *pieces_to_host(const std::vector<HostPiece> &pieces, int n, int m, i64 prime)
 {
+	cudaStream_t s = ctx().stream;
 	i64 total = 0;
 	for (const HostPiece &pc : pieces)
-		total += (i64) pc.j.size();
+		total += pc.nnz;
 	struct spasm_csr *H = spasm_csr_alloc(n, m, std::max<i64>(total, 1), prime, true);
 	i64 off = 0;
 	int row = 0;
+	std::vector<i64> hp;
 	for (const HostPiece &pc : pieces) {
-		int rows = (int) pc.p.size() - 1;
-		for (int t = 0; t < rows; t++)
-			H->p[row + t + 1] = off + pc.p[t + 1];
-		memcpy(H->j + off, pc.j.data(), pc.j.size() * sizeof(int));
-		memcpy(H->x + off, pc.x.data(), pc.x.size() * sizeof(i32));
-		off += (i64) pc.j.size();
-		row += rows;
+		hp.resize((size_t) pc.rows + 1);
+		pc.p.download(hp.data(), hp.size(), s);
+		pc.j.download(H->j + off, (size_t) pc.nnz, s);
+		pc.x.download(H->x + off, (size_t) pc.nnz, s);
+		sync();
+		for (int t = 0; t < pc.rows; t++)
+			H->p[row + t + 1] = off + hp[t + 1];
+		off += pc.nnz;
+		row += pc.rows;
+		stats().pub.d2h_bytes += pc.nnz * 8 + (i64) (pc.rows + 1) * 8;
 	}
 	for (; row < n; row++)
 		H->p[row + 1] = off;
-	spasm_csr_realloc(H, -1);
 	return H;
 }
 

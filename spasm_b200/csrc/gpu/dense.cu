@@ -235,19 +235,21 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 			s_pcol[s_k] = c;
 			s_k += 1;
 			taken[piv] = 1;
-			s_inv = zp_inverse(Pw[piv * PSTRIDE + c], F);
 		}
 		__syncthreads();
-		const i32 inv = s_inv;
+		/* Fraction-free elimination: row_i <- d * row_i - l * row_piv.  Only the zero pattern matters here (which
+		 * rows and columns are pivots); scaling a row by the unit d does not change it, and no modular inverse sits
+		 * on the critical path of the 32 steps.  |d * x - l * y| < 2^63 for balanced residues below 2^31. */
+		const i64 d = Pw[piv * PSTRIDE + c];
 		for (int i = tid; i < n; i += T) {
 			if (taken[i])
 				continue;
-			i32 l = Pw[i * PSTRIDE + c];
+			const i64 l = Pw[i * PSTRIDE + c];
 			if (l == 0)
 				continue;
-			l = zp_mul(l, inv, F);
-			for (int cc = c; cc < nbw; cc++)
-				Pw[i * PSTRIDE + cc] = zp_reduce((i64) Pw[i * PSTRIDE + cc] - (i64) l * Pw[piv * PSTRIDE + cc], F);
+			Pw[i * PSTRIDE + c] = 0;
+			for (int cc = c + 1; cc < nbw; cc++)
+				Pw[i * PSTRIDE + cc] = zp_reduce(d * Pw[i * PSTRIDE + cc] - l * Pw[piv * PSTRIDE + cc], F);
 		}
 		__syncthreads();
 	}
@@ -258,7 +260,9 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 	if (k == 0)
 		return;
 
-	/* --- M^-1 by Gauss-Jordan on [M | I] */
+	/* --- M^-1 by fraction-free Gauss-Jordan on [M | I]: row_s <- d * row_s - l * row_t keeps every step free of
+	 * modular inverses (which are ~1 us each on one thread); at the end the left half is diagonal and the k
+	 * inverses of the diagonal are computed by k threads at once. */
 	for (int idx = tid; idx < k * 2 * NB; idx += T) {
 		int s = idx / (2 * NB), t = idx % (2 * NB);
 		i64 v = 0;
@@ -274,33 +278,49 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 			int s = t;
 			while (Mw[s][t] == 0)
 				s++;                         /* M is invertible: a non-zero entry exists below */
-			if (s != t)
-				for (int c = 0; c < 2 * NB; c++) {
-					i64 tmp = Mw[s][c];
-					Mw[s][c] = Mw[t][c];
-					Mw[t][c] = tmp;
-				}
-			s_inv = zp_inverse((i32) Mw[t][t], F);
+			s_min = s;
 		}
 		__syncthreads();
-		if (tid < 2 * NB)
-			Mw[t][tid] = zp_mul((i32) Mw[t][tid], s_inv, F);
-		__syncthreads();
-		for (int idx = tid; idx < k * 2 * NB; idx += T) {
-			int s = idx / (2 * NB), c = idx % (2 * NB);
-			if (s == t)
-				continue;
-			i64 l = Mw[s][t];
-			/* all threads of row s read Mw[s][t] before any of them rewrites it: column t is rewritten by c == t only */
-			if (l != 0 && c != t)
-				Mw[s][c] = zp_reduce(Mw[s][c] - l * Mw[t][c], F);
+		const int sw = s_min;
+		if (sw != t && tid < 2 * NB) {
+			i64 tmp = Mw[sw][tid];
+			Mw[sw][tid] = Mw[t][tid];
+			Mw[t][tid] = tmp;
 		}
 		__syncthreads();
-		for (int s = tid; s < k; s += T)
-			if (s != t)
-				Mw[s][t] = 0;
+		/* every thread takes its operands (the multiplier column t and the pivot row t are rewritten below) */
+		i64 l0 = 0, l1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+		const i64 d = Mw[t][t];
+		const int idx0 = tid, idx1 = tid + T;
+		const int sa = idx0 / (2 * NB), ca = idx0 % (2 * NB), sb2 = idx1 / (2 * NB), cb = idx1 % (2 * NB);
+		const bool doa = idx0 < k * 2 * NB && sa != t, dob = idx1 < k * 2 * NB && sb2 != t;
+		if (doa) {
+			l0 = Mw[sa][t];
+			x0 = Mw[sa][ca];
+			y0 = Mw[t][ca];
+		}
+		if (dob) {
+			l1 = Mw[sb2][t];
+			x1 = Mw[sb2][cb];
+			y1 = Mw[t][cb];
+		}
+		__syncthreads();
+		if (doa && l0 != 0)
+			Mw[sa][ca] = (ca == t) ? 0 : (i64) zp_reduce(d * x0 - l0 * y0, F);
+		if (dob && l1 != 0)
+			Mw[sb2][cb] = (cb == t) ? 0 : (i64) zp_reduce(d * x1 - l1 * y1, F);
 		__syncthreads();
 	}
+	/* scale row s by the inverse of its diagonal entry */
+	__shared__ i32 s_dinv[NB];
+	if (tid < k)
+		s_dinv[tid] = zp_inverse((i32) Mw[tid][tid], F);
+	__syncthreads();
+	for (int idx = tid; idx < k * NB; idx += T) {
+		int s = idx / NB, c = idx % NB;
+		Mw[s][NB + c] = zp_mul((i32) Mw[s][NB + c], s_dinv[s], F);
+	}
+	__syncthreads();
 
 	/* --- hand M^-1 to the multiplier kernel (the n x k x k product is spread over the whole GPU) */
 	for (int idx = tid; idx < NB * NB; idx += T) {

@@ -80,6 +80,18 @@ __host__ __device__ __forceinline__ int32_t zp_add(int32_t a, int32_t b, const Z
 /* extended Euclid, same element as the reference's spasm_ZZp_inverse (ZZp.c:49-74) */
 __host__ __device__ inline int32_t zp_inverse(int32_t a, const Zp &F)
 {
+#ifdef __CUDA_ARCH__
+	/* same remainder sequence with 32-bit unsigned divisions (p < 2^32): a 64-bit division is a ~100-instruction
+	 * routine on the GPU and this runs on the critical path of the dense panel kernel */
+	uint32_t u0 = (uint32_t) F.p, u1 = (uint32_t) (a < 0 ? (int64_t) a + F.p : (int64_t) a);
+	int64_t s0 = 0, s1 = 1;
+	while (u1 != 0) {
+		uint32_t q = u0 / u1, u2 = u0 - q * u1;
+		int64_t s2 = s0 - (int64_t) q * s1;
+		u0 = u1; u1 = u2; s0 = s1; s1 = s2;
+	}
+	return zp_reduce(s0, F);
+#endif
 	int64_t r0 = F.p, r1 = a < 0 ? (int64_t) a + F.p : a, t0 = 0, t1 = 1;
 	while (r1 != 0) {
 		int64_t q = r0 / r1;
