@@ -316,13 +316,24 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 	spasm_human_format(spasm_nnz(U), hnnz);
 	LOG("[rref] start. U is %d x %d (%s nnz)\n", n, m, hnnz);
 	ctx();
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sb::sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace] rref/%-22s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	Engine E;
 	engine_from_host(E, U, fact->qinv);
+	lap("upload + schedule");
 	cudaStream_t s = ctx().stream;
 	std::vector<int> pivcol((size_t) std::max(n, 1));
 	for (int i = 0; i < n; i++)
 		pivcol[i] = U->j[U->p[i]];
-	const int cap = panel_capacity(m);
+	const int cap = panel_capacity(m, 64.0);
 	std::vector<HostPiece> pieces;
 	for (int done = 0; done < n; done += cap) {
 		int R = std::min(cap, n - done);
@@ -334,7 +345,8 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 		d_first.upload(pivcol.data() + done, (size_t) R, s);
 		/* row i is solved against U with its own pivot unregistered (rref.c:56-60): its pivot entry is not
 		 * scattered, so nothing propagates from it, and it is emitted first, as 1 */
-		E.solve_rows(E.U, d_rows.ptr, R, true);
+		E.solve_rows(E.U, d_rows.ptr, R, true, true);      /* rows of the RREF are very sparse: masked solve */
+		lap("solve");
 		DevBuf<i64> Sp;
 		DevBuf<int> Sj;
 		DevBuf<i32> Sx;
@@ -342,8 +354,10 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 		panel_to_csr(E.panel, E.Uqinv.ptr, d_first.ptr, 1, nullptr, Sp, Sj, Sx, nnz);
 		pieces.emplace_back();
 		piece_download(Sp, Sj, Sx, R, nnz, pieces.back());
+		lap("panel -> sparse rows");
 	}
 	struct spasm_csr *Rm = pieces_to_host(pieces, n, m, spasm_get_prime(U));
+	lap("download");
 	for (int j = 0; j < m; j++)
 		Rqinv[j] = -1;
 	for (int i = 0; i < n; i++)
@@ -381,7 +395,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact)
 	for (int j = 0; j < m; j++)
 		if (qinv[j] < 0)
 			freecols.push_back(j);
-	const int cap = panel_capacity(std::max(n, 1));
+	const int cap = panel_capacity(std::max(n, 1), 64.0);
 	std::vector<HostPiece> pieces;
 	std::vector<int> colslot((size_t) std::max(m, 1));
 	Panel P;

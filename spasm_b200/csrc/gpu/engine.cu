@@ -48,17 +48,25 @@ void Engine::begin_dense()
 	dense_ready = true;
 }
 
-void Engine::solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first)
+void Engine::solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first, bool sparse_batch)
 {
 	if (!G_ready)
 		rebuild_schedule();
 	GpuTimer t;
 	t.start();
-	panel.shape(m, R);
+	/* Opt-in (SPASM_B200_MASKED_SOLVE=1): on the 500k x 500k configuration the eliminations of a row of the RREF
+	 * reach a large share of the pivots, the masks are dense and the plain solve is 5 times faster. */
+	static const bool use_mask = getenv("SPASM_B200_MASKED_SOLVE") != NULL;
+	const bool masked = sparse_batch && use_mask;
+	panel.shape(m, R, masked);
 	panel_scatter_rows(B, d_rows, R, panel, F, skip_first);
-	panel_solve(G, panel.X, panel.ld, R, F);
+	if (masked)
+		panel_solve_masked(G, panel.X, panel.ld, R, panel.mask.ptr, panel.mw, F);
+	else
+		panel_solve(G, panel.X, panel.ld, R, F);
 	stats().pub.ms_solve += t.stop_ms();
-	account_bytes(R);
+	if (!masked)
+		account_bytes(R);
 }
 
 void Engine::solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w)

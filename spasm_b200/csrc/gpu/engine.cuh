@@ -48,7 +48,7 @@ struct Engine {
 	int rank() const { return U.n + dense_rank; }
 
 	/* solve the rows `rows` (indices into B) against the structural U: results in panel */
-	void solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first);
+	void solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_first, bool sparse_batch = false);
 	void solve_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w);
 	/* dense block (R x Sm0, ld = ldB, room for world * chunk rows) of the rows / combinations reduced by the structural
 	 * pivots; with several ranks each one solves a slice and the slices are all-gathered */

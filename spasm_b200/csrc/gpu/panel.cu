@@ -4,7 +4,7 @@
 
 namespace sb {
 
-void Panel::shape(int nnodes_, int R_)
+void Panel::shape(int nnodes_, int R_, bool masked_)
 {
 	nnodes = nnodes_;
 	R = R_;
@@ -13,11 +13,16 @@ void Panel::shape(int nnodes_, int R_)
 		ld = 4;
 	X.ensure((size_t) std::max(nnodes, 1) * ld);
 	CUDA_CHECK(cudaMemsetAsync(X.ptr, 0, (size_t) std::max(nnodes, 1) * ld * sizeof(i32), ctx().stream));
+	masked = masked_;
+	mw = masked ? (ld / 4 + 31) / 32 : 0;
+	if (masked) {
+		mask.ensure((size_t) std::max(nnodes, 1) * mw);
+		CUDA_CHECK(cudaMemsetAsync(mask.ptr, 0, (size_t) std::max(nnodes, 1) * mw * sizeof(unsigned), ctx().stream));
+	}
 }
 
-int panel_capacity(int nnodes)
+int panel_capacity(int nnodes, double gb)
 {
-	double gb = 16.0;
 	const char *s = getenv("SPASM_B200_PANEL_GB");
 	if (s)
 		gb = atof(s);
@@ -30,14 +35,17 @@ int panel_capacity(int nnodes)
 /* ------------------------------------------------------------------ scatter */
 
 __global__ void k_scatter_rows(int R, const int *__restrict__ rows, const i64 *__restrict__ Bp, const int *__restrict__ Bj,
-                               const i32 *__restrict__ Bx, i32 *X, int ld, Zp F, int skip_first)
+                               const i32 *__restrict__ Bx, i32 *X, int ld, Zp F, int skip_first, unsigned *mask, int mw)
 {
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
 	for (int r = warp; r < R; r += nwarps) {
 		int i = rows[r];
-		for (i64 k = Bp[i] + skip_first + lane; k < Bp[i + 1]; k += 32)
+		for (i64 k = Bp[i] + skip_first + lane; k < Bp[i + 1]; k += 32) {
 			zp_atomic_add(&X[(size_t) Bj[k] * ld + r], Bx[k], F);
+			if (mask)
+				atomicOr(&mask[(size_t) Bj[k] * mw + (r >> 7)], 1u << ((r >> 2) & 31));
+		}
 	}
 }
 
@@ -45,7 +53,8 @@ void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, con
 {
 	if (R == 0)
 		return;
-	k_scatter_rows<<<std::min(cdiv((size_t) R * 32, 256), 148u * 16), 256, 0, ctx().stream>>>(R, d_rows, B.p, B.j, B.x, P.X, P.ld, F, skip_first ? 1 : 0);
+	k_scatter_rows<<<std::min(cdiv((size_t) R * 32, 256), 148u * 16), 256, 0, ctx().stream>>>(R, d_rows, B.p, B.j, B.x, P.X, P.ld, F, skip_first ? 1 : 0,
+	                                                                                             P.masked ? P.mask.ptr : nullptr, P.mw);
 	LAUNCHED(1);
 	KERNEL_CHECK();
 }
@@ -133,7 +142,8 @@ void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS)
  * entries of (chunk, r) when part != NULL, or emits them when Sj != NULL */
 template <bool EMIT>
 __global__ void k_panel_sparse(int nnodes, int R, const i32 *__restrict__ X, int ld, const int *__restrict__ flag,
-                               int *part, const i64 *__restrict__ Sp, const int *__restrict__ node_to_col, int *Sj, i32 *Sx, int has_first)
+                               int *part, const i64 *__restrict__ Sp, const int *__restrict__ node_to_col, int *Sj, i32 *Sx, int has_first,
+                               const unsigned *__restrict__ mask, int mw)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= R)
@@ -144,6 +154,9 @@ __global__ void k_panel_sparse(int nnodes, int R, const i32 *__restrict__ X, int
 	i64 base = EMIT ? Sp[r] + has_first + part[(size_t) chunk * R + r] : 0;
 	for (int c = c0; c < c1; c++) {
 		if (flag && flag[c] >= 0)
+			continue;
+		/* masked panels: one word per 128 right-hand sides says which groups of 4 can be non-zero (a warp reads one word) */
+		if (mask && !((mask[(size_t) c * mw + (r >> 7)] >> ((r >> 2) & 31)) & 1u))
 			continue;
 		i32 v = X[(size_t) c * ld + r];
 		if (v == 0)
@@ -204,7 +217,8 @@ i64 panel_count_nonzero(const Panel &P, const int *d_flag)
 	DevBuf<unsigned long long> total(1);
 	total.zero(s);
 	dim3 grid(cdiv(P.R, 128), nchunks);
-	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, P.R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0);
+	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, P.R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0,
+	                                           P.masked ? P.mask.ptr : nullptr, P.mw);
 	k_chunk_prefix<<<cdiv(P.R, 128), 128, 0, s>>>(nchunks, P.R, part.ptr, rowlen.ptr, 0);
 	k_sum_i64<<<std::min(cdiv(P.R, 256), 64u), 256, 0, s>>>(P.R, rowlen.ptr, total.ptr);
 	LAUNCHED(3);
@@ -229,7 +243,8 @@ void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32
 	DevBuf<i64> rowlen((size_t) R + 1);
 	rowlen.zero(s);
 	dim3 grid(cdiv(R, 128), nchunks);
-	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0);
+	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0,
+	                                           P.masked ? P.mask.ptr : nullptr, P.mw);
 	k_chunk_prefix<<<cdiv(R, 128), 128, 0, s>>>(nchunks, R, part.ptr, rowlen.ptr, has_first);
 	static DevBuf<char> tmp;
 	size_t bytes = 0;
@@ -241,7 +256,8 @@ void panel_to_csr(const Panel &P, const int *d_flag, const int *d_first_col, i32
 	Sj.alloc((size_t) std::max<i64>(nnz, 1));
 	Sx.alloc((size_t) std::max<i64>(nnz, 1));
 	if (nnz > 0 && !count_only) {
-		k_panel_sparse<true><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, Sp.ptr, d_node_to_col, Sj.ptr, Sx.ptr, has_first);
+		k_panel_sparse<true><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, Sp.ptr, d_node_to_col, Sj.ptr, Sx.ptr, has_first,
+		                                          P.masked ? P.mask.ptr : nullptr, P.mw);
 		LAUNCHED(1);
 		if (has_first) {
 			k_emit_first<<<cdiv(R, 128), 128, 0, s>>>(R, Sp.ptr, d_first_col, first_val, Sj.ptr, Sx.ptr);

@@ -13,11 +13,20 @@ namespace sb {
 struct Panel {
 	DevBuf<i32> X;
 	int nnodes = 0, ld = 0, R = 0;
-	void shape(int nnodes_, int R_);     /* (re)allocate and zero */
+	/* optional occupancy mask for very sparse batches (spasm_rref): bit g of node c = the group of 4 right-hand sides
+	 * 4g..4g+3 of X[c] may be non-zero.  mw words per node; the scatter sets the bits of the right-hand sides, the
+	 * solve propagates them (OR over the dependencies) and computes the marked groups only, the conversion back to
+	 * sparse rows reads the marked groups only. */
+	DevBuf<unsigned> mask;
+	int mw = 0;
+	bool masked = false;
+	void shape(int nnodes_, int R_, bool masked_ = false);     /* (re)allocate and zero */
 };
 
-/* how many right-hand sides fit the panel budget for this many nodes */
-int panel_capacity(int nnodes);
+/* how many right-hand sides fit the panel budget (GB of HBM, SPASM_B200_PANEL_GB overrides) for this many nodes.
+ * A solve costs about the same whatever its width (it is bound by the depth of the pivot DAG), so callers that own
+ * the whole device (rref, kernel) ask for a large panel. */
+int panel_capacity(int nnodes, double gb = 16.0);
 
 /* X[B.j[e]][r] += B.x[e] for every entry e of row rows[r] (r < R); skip_first drops the first entry of each row */
 void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first);

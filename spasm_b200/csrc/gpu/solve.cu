@@ -597,18 +597,44 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 				int4 b = Xc[r];
 				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
 				int pendingred = 0;
-				for (int e = 0; e < cnt; e++) {
+				int e = 0;
+				/* four dependencies at a time: their 16-byte loads are independent and in flight together (wide
+				 * batches are bound by the bytes in flight per SM, not by the arithmetic) */
+				for (; F.delay >= 4 && e + 4 <= cnt; e += 4) {
+					i64 v[4];
+					int4 xs[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const int sc = (e + u < cached) ? cur.src[e + u] : src[e0 + e + u];
+						v[u] = (e + u < cached) ? cur.val[e + u] : val[e0 + e + u];
+						xs[u] = __ldcg(&X[(size_t) sc * ld4 + r]);
+					}
+					if (pendingred + 4 > F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pendingred = 0;
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						a0 -= v[u] * xs[u].x;
+						a1 -= v[u] * xs[u].y;
+						a2 -= v[u] * xs[u].z;
+						a3 -= v[u] * xs[u].w;
+					}
+					pendingred += 4;
+				}
+				for (; e < cnt; e++) {
 					const i64 v = (e < cached) ? cur.val[e] : val[e0 + e];
 					const int sc = (e < cached) ? cur.src[e] : src[e0 + e];
 					const int4 xs = __ldcg(&X[(size_t) sc * ld4 + r]);
+					if (pendingred + 1 > F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pendingred = 0;
+					}
 					a0 -= v * xs.x;
 					a1 -= v * xs.y;
 					a2 -= v * xs.z;
 					a3 -= v * xs.w;
-					if (++pendingred == F.delay) {
-						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
-						pendingred = 0;
-					}
+					pendingred++;
 				}
 				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
 				Xc[r] = b;
@@ -636,6 +662,152 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 			atomicAdd(done, 1);
 		__syncthreads();
 	}
+}
+
+/* Dataflow solve of a very sparse batch (spasm_rref: a row of the RREF touches a fraction of a percent of the
+ * columns).  Same schedule as k_panel_solve_flow; per column the CTA first ORs the occupancy masks of the column and
+ * of its dependencies (mw words: 128 right-hand sides per word), lists the marked groups in shared memory and computes
+ * those only.  The traffic is the masks (1/128 of the panel) plus the marked groups. */
+__global__ void __launch_bounds__(1024)
+k_panel_solve_flow_masked(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+                          const i64 *__restrict__ rptr, const int *__restrict__ rdst, int *pending, int *queue, int nscheduled,
+                          int *tail, int *ticket, int *done, int *error, int4 *X, int ld4, int R4, unsigned *mask, int mw, Zp F)
+{
+	extern __shared__ int s_list[];      /* marked groups of the current column (at most R4) */
+	__shared__ int s_node, s_next, s_count;
+	const int tid = threadIdx.x, T = blockDim.x;
+	int next = -1;
+	for (;;) {
+		if (tid == 0) {
+			int got = next;
+			if (got < 0) {
+				const int t = atomicAdd(ticket, 1);
+				got = -2;
+				for (long spin = 0;; spin++) {
+					if (t < nscheduled) {
+						got = *((volatile int *) &queue[t]);
+						if (got >= 0)
+							break;
+					}
+					if (*((volatile int *) done) >= nscheduled || *((volatile int *) error)) {
+						got = -2;
+						break;
+					}
+					if (spin > (1L << 24)) {
+						*error = 1;
+						got = -2;
+						break;
+					}
+					__nanosleep(100);
+				}
+			}
+			s_node = got;
+			s_count = 0;
+			s_next = -1;
+		}
+		__syncthreads();
+		const int c = s_node;
+		if (c < 0)
+			return;
+		const i64 e0 = ptr[c];
+		const int cnt = (int) (ptr[c + 1] - e0);
+		/* ---- occupancy of the column: its right-hand sides or any dependency */
+		for (int w = tid; w < mw; w += T) {
+			unsigned m = mask[(size_t) c * mw + w];
+			for (int e = 0; e < cnt; e++)
+				m |= __ldcg(&mask[(size_t) src[e0 + e] * mw + w]);
+			mask[(size_t) c * mw + w] = m;
+			while (m) {
+				const int b = __ffs(m) - 1;
+				m &= m - 1;
+				s_list[atomicAdd(&s_count, 1)] = w * 32 + b;
+			}
+		}
+		__syncthreads();
+		const int ngroups = s_count;
+		/* ---- the marked groups; dependencies are read around L1 (written by other SMs) */
+		int4 *Xc = X + (size_t) c * ld4;
+		for (int t = tid; t < ngroups; t += T) {
+			const int g = s_list[t];
+			int4 b = Xc[g];
+			i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+			int pendingred = 0;
+			for (int e = 0; e < cnt; e++) {
+				const i64 v = val[e0 + e];
+				const int4 xs = __ldcg(&X[(size_t) src[e0 + e] * ld4 + g]);
+				a0 -= v * xs.x;
+				a1 -= v * xs.y;
+				a2 -= v * xs.z;
+				a3 -= v * xs.w;
+				if (++pendingred == F.delay) {
+					a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+					pendingred = 0;
+				}
+			}
+			b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
+			Xc[g] = b;
+		}
+		__threadfence();
+		__syncthreads();
+		/* ---- release the dependents; keep one as the next job of this CTA */
+		const i64 rb = rptr[c], re = rptr[c + 1];
+		for (i64 k = rb + tid; k < re; k += T) {
+			const int d = rdst[k];
+			if (atomicSub(&pending[d], 1) == 1) {
+				if (atomicCAS(&s_next, -1, d) != -1) {
+					const int pos = atomicAdd(tail, 1);
+					__threadfence();
+					*((volatile int *) &queue[pos]) = d;
+				}
+			}
+		}
+		__syncthreads();
+		next = s_next;
+		if (tid == 0)
+			atomicAdd(done, 1);
+		__syncthreads();
+	}
+}
+
+void panel_solve_masked(const DepGraph &G, i32 *X, int ld, int R, unsigned *mask, int mw, const Zp &F)
+{
+	if (G.nlevels <= 1 || R <= 0 || G.nscheduled <= 0)
+		return;
+	if (ld % 4 != 0)
+		errx(1, "[spasm-b200] internal: panel leading dimension must be a multiple of 4");
+	int R4 = (R + 3) / 4, ld4 = ld / 4;
+	cudaStream_t s = ctx().stream;
+	int n = G.nnodes;
+	DevBuf<int> pending((size_t) n), queue((size_t) n + 1), counters(4);
+	CUDA_CHECK(cudaMemcpyAsync(pending.ptr, G.pending0.ptr, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+	queue.fill_byte(0xff, s);
+	CUDA_CHECK(cudaMemcpyAsync(queue.ptr, G.seeds.ptr, (size_t) G.nseeds * sizeof(int), cudaMemcpyDeviceToDevice, s));
+	int h_init[4] = {G.nseeds, 0, 0, 0};      /* tail, ticket, done, error */
+	CUDA_CHECK(cudaMemcpyAsync(counters.ptr, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
+	const int threads = 256;
+	size_t smem = (size_t) mw * 32 * sizeof(int);
+	CUDA_CHECK(cudaFuncSetAttribute(k_panel_solve_flow_masked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow_masked, threads, smem));
+	if (occ < 1)
+		errx(1, "[spasm-b200] internal: masked solve kernel does not fit (%zu bytes of shared memory)", smem);
+	int blocks = std::min(occ, 8) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
+	GpuTimer tk;
+	tk.start();
+	k_panel_solve_flow_masked<<<blocks, threads, smem, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
+	                                                       G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3,
+	                                                       (int4 *) X, ld4, R4, mask, mw, F);
+	LAUNCHED(1);
+	KERNEL_CHECK();
+	stats().pub.ms_k_panel_solve += tk.stop_ms();
+	int h[4];
+	CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+	sync();
+	if (h[3] != 0 || h[2] != G.nscheduled)
+		errx(1, "[spasm-b200] internal: masked dataflow solve did not complete (%d of %d columns)", h[2], G.nscheduled);
+	Stats &st = stats();
+	st.pub.solve_batches += 1;
+	st.pub.solve_rows += R;
 }
 
 void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)

@@ -62,5 +62,9 @@ void depgraph_schedule(DepGraph &G);
 
 /* X is nnodes x ld (ld multiple of 4, >= R), int32 balanced, column-major per node; solved in place */
 void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F);
+/* same solve for a very sparse batch: mask (nnodes x mw words, bit g of a node = its group of right-hand sides
+ * 4g..4g+3 may be non-zero) holds the pattern of the right-hand sides on entry and of the solution on exit; only the
+ * marked groups are computed (the others are zero and stay untouched) */
+void panel_solve_masked(const DepGraph &G, i32 *X, int ld, int R, unsigned *mask, int mw, const Zp &F);
 
 }  // namespace sb
