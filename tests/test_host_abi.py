@@ -190,8 +190,10 @@ def test_default_options_match_reference(product):
 
 def test_tensor_core_path_is_really_tcgen05():
     """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTC*MMA (UTCIMMA for kind::i8), tcgen05.ld -> LDTM,
-    tcgen05.commit -> UTCBAR in the built library; no legacy HMMA/IMMA tensor path."""
+    tcgen05.commit -> UTCBAR, cp.async.bulk (the operand pipeline of the packed kernel) -> UBLKCP in the built library;
+    no legacy HMMA/IMMA tensor path."""
     sass = subprocess.run(["cuobjdump", "-sass", spasm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCIMMA" in sass, "no tcgen05.mma kind::i8 in the SASS"
     assert "LDTM" in sass and "UTCBAR" in sass
+    assert "UBLKCP" in sass, "no bulk-copy (TMA engine) operand pipeline in the SASS"
     assert " IMMA." not in sass and " HMMA." not in sass
