@@ -48,7 +48,7 @@ Stats &stats();
  * made the download of a 2.4 GB echelon form cost more than its computation.  download_bulk asks for huge pages on
  * the destination, copies chunk by chunk into pinned staging buffers and lets several host threads move each chunk
  * to its place (they take the page faults in parallel) while the next chunk is in flight. */
-static const size_t BULK_DOWNLOAD_BYTES = (size_t) 16 << 20;
+size_t bulk_download_threshold();      /* 16 MB; SPASM_B200_BULK_MB overrides (read at every call: the tests toggle it) */
 void download_bulk(void *host, const void *dev, size_t bytes);
 
 /* -------------------------------------------------------------------- device buffers */
@@ -93,7 +93,7 @@ template <typename T> struct DevBuf {
 	}
 	/* small transfers are asynchronous on s; large ones take the staged path (download_bulk) and are complete on return */
 	void download(T *host, size_t n, cudaStream_t s) const {
-		if (n * sizeof(T) >= BULK_DOWNLOAD_BYTES)
+		if (n * sizeof(T) >= bulk_download_threshold())
 			download_bulk(host, ptr, n * sizeof(T));
 		else if (n)
 			CUDA_CHECK(cudaMemcpyAsync(host, ptr, n * sizeof(T), cudaMemcpyDeviceToHost, s));

@@ -56,7 +56,7 @@ void Engine::solve_rows(const DevCsr &B, const int *d_rows, int R, bool skip_fir
 	t.start();
 	/* Opt-in (SPASM_B200_MASKED_SOLVE=1): on the 500k x 500k configuration the eliminations of a row of the RREF
 	 * reach a large share of the pivots, the masks are dense and the plain solve is 5 times faster. */
-	static const bool use_mask = getenv("SPASM_B200_MASKED_SOLVE") != NULL;
+	const bool use_mask = getenv("SPASM_B200_MASKED_SOLVE") != NULL;       /* read at every call: the tests toggle it */
 	const bool masked = sparse_batch && use_mask;
 	panel.shape(m, R, masked);
 	panel_scatter_rows(B, d_rows, R, panel, F, skip_first);

@@ -195,3 +195,46 @@ def test_out_of_order_greedy_search_is_deterministic_under_repetition():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l and l[0].isdigit()]
     assert len(lines) == 120 and all(l.endswith("same") for l in lines), out.stdout[-2000:]
+
+
+def _echelon_arrays(product, A, **kw):
+    oracle.reset_rand()
+    f = host.echelonize(product, A, host.default_opts(product, **kw))
+    U = f.U
+    return f, (f.rank, U["p"].tobytes(), U["j"].tobytes(), U["x"].tobytes(), f.qinv.tobytes())
+
+
+def test_staged_download_of_large_results_is_transparent(product, monkeypatch):
+    """Results above 16 MB leave the device through pinned staging buffers and several copy threads (download_bulk);
+    forcing that path on a small result (threshold 4 KB, chunks still 32 MB) and forbidding it must give the same
+    arrays, for the echelon form, the RREF and the kernel basis."""
+    t = synthetic.config3(0.02)
+    A = host.compress(product, t)
+    out = {}
+    for tag, mb in (("plain", "1000000"), ("staged", "0.004")):
+        monkeypatch.setenv("SPASM_B200_BULK_MB", mb)
+        f, arrays = _echelon_arrays(product, A, sparsity_threshold=0.01)
+        R, _ = host.rref(product, f)
+        K = host.kernel(product, f)
+        Rn, Kn = R.numpy(), K.numpy()
+        out[tag] = (arrays, Rn["p"].tobytes(), Rn["j"].tobytes(), Rn["x"].tobytes(), Kn["p"].tobytes(), Kn["j"].tobytes(), Kn["x"].tobytes())
+    assert out["plain"] == out["staged"]
+
+
+def test_masked_solve_gives_the_same_rref(product, monkeypatch):
+    """spasm_rref through the occupancy-masked dataflow solve (opt-in, SPASM_B200_MASKED_SOLVE=1) and through the
+    plain solve: identical matrices, entry order included."""
+    for t, kw in ((synthetic.config1(0.1), {}), (synthetic.config4(0.01), {}), (synthetic.config2(0.02).transposed(), {})):
+        A = host.compress(product, t)
+        f, _ = _echelon_arrays(product, A, **kw)
+        res = {}
+        for tag in ("plain", "masked"):
+            if tag == "masked":
+                monkeypatch.setenv("SPASM_B200_MASKED_SOLVE", "1")
+            else:
+                monkeypatch.delenv("SPASM_B200_MASKED_SOLVE", raising=False)
+            R, Rqinv = host.rref(product, f)
+            Rn = R.numpy()
+            res[tag] = (Rn["p"].tobytes(), Rn["j"].tobytes(), Rn["x"].tobytes(), np.asarray(Rqinv).tobytes())
+        monkeypatch.delenv("SPASM_B200_MASKED_SOLVE", raising=False)
+        assert res["plain"] == res["masked"]
