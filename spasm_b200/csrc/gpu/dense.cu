@@ -1,3 +1,4 @@
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include "dense.cuh"
 #include "stats.cuh"
@@ -175,6 +176,90 @@ struct PanelInfo {
 	i32 Minv[NB][NB];      /* inverse of S[prow, c0 + pcol] */
 };
 
+/* Common tail of the panel kernels (whole CTA): M^-1 for M = S[prow, c0 + pcol] (k x k, original values), then the new
+ * pivots are recorded (rowstate, pivcol list, rank counter) and M^-1 is handed to the multiplier kernel. */
+__device__ void panel_invert_and_publish(const i32 *__restrict__ S, int ld, int c0, int k, int r0, int *s_prow, int *s_pcol,
+                                         i64 (*Mw)[2 * NB + 1], i32 *s_dinv, int *s_sw, int *rowstate, int *rank_dev, int *pivcol_out,
+                                         PanelInfo *info, const Zp &F)
+{
+	const int tid = threadIdx.x, T = blockDim.x;
+	/* --- M^-1 by fraction-free Gauss-Jordan on [M | I]: row_s <- d * row_s - l * row_t keeps every step free of
+	 * modular inverses (which are ~1 us each on one thread); at the end the left half is diagonal and the k
+	 * inverses of the diagonal are computed by k threads at once. */
+	for (int idx = tid; idx < k * 2 * NB; idx += T) {
+		int s = idx / (2 * NB), t = idx % (2 * NB);
+		i64 v = 0;
+		if (t < k)
+			v = S[(size_t) s_prow[s] * ld + c0 + s_pcol[t]];
+		else if (t >= NB)
+			v = (t - NB == s);
+		Mw[s][t] = v;
+	}
+	__syncthreads();
+	for (int t = 0; t < k; t++) {
+		if (tid == 0) {
+			int s = t;
+			while (Mw[s][t] == 0)
+				s++;                         /* M is invertible: a non-zero entry exists below */
+			*s_sw = s;
+		}
+		__syncthreads();
+		const int sw = *s_sw;
+		if (sw != t && tid < 2 * NB) {
+			i64 tmp = Mw[sw][tid];
+			Mw[sw][tid] = Mw[t][tid];
+			Mw[t][tid] = tmp;
+		}
+		__syncthreads();
+		/* every thread takes its operands (the multiplier column t and the pivot row t are rewritten below) */
+		constexpr int PER = 8;                 /* NB * 2NB = 2048 entries, at least 256 threads */
+		i64 lv[PER], xv[PER], yv[PER];
+		const i64 d = Mw[t][t];
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			const int idx = tid + u * T, sa = idx / (2 * NB), ca = idx % (2 * NB);
+			lv[u] = 0;
+			if (idx < k * 2 * NB && sa != t) {
+				lv[u] = Mw[sa][t];
+				xv[u] = Mw[sa][ca];
+				yv[u] = Mw[t][ca];
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			const int idx = tid + u * T, sa = idx / (2 * NB), ca = idx % (2 * NB);
+			if (lv[u] != 0)
+				Mw[sa][ca] = (ca == t) ? 0 : (i64) zp_reduce(d * xv[u] - lv[u] * yv[u], F);
+		}
+		__syncthreads();
+	}
+	/* scale row s by the inverse of its diagonal entry */
+	if (tid < k)
+		s_dinv[tid] = zp_inverse((i32) Mw[tid][tid], F);
+	__syncthreads();
+	for (int idx = tid; idx < k * NB; idx += T) {
+		int s = idx / NB, c = idx % NB;
+		Mw[s][NB + c] = zp_mul((i32) Mw[s][NB + c], s_dinv[s], F);
+	}
+	__syncthreads();
+
+	/* --- hand M^-1 to the multiplier kernel (the n x k x k product is spread over the whole GPU) */
+	for (int idx = tid; idx < NB * NB; idx += T) {
+		int s = idx / NB, t = idx % NB;
+		info->Minv[s][t] = (s < k && t < k) ? (i32) Mw[s][NB + t] : 0;
+	}
+	if (tid < k) {
+		info->prow[tid] = s_prow[tid];
+		info->pcol[tid] = s_pcol[tid];
+		rowstate[s_prow[tid]] = r0 + tid;
+		pivcol_out[r0 + tid] = c0 + s_pcol[tid];
+	}
+	__syncthreads();
+	if (tid == 0)
+		*rank_dev = r0 + k;
+}
+
 /*
  * One CTA.  Works on a private copy of the panel S[:, c0:c0+nb]:
  *   1. discovers the pivots of the panel by forward elimination on the rows that are not pivotal yet
@@ -260,82 +345,120 @@ k_rref_panel(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowst
 	if (k == 0)
 		return;
 
-	/* --- M^-1 by fraction-free Gauss-Jordan on [M | I]: row_s <- d * row_s - l * row_t keeps every step free of
-	 * modular inverses (which are ~1 us each on one thread); at the end the left half is diagonal and the k
-	 * inverses of the diagonal are computed by k threads at once. */
-	for (int idx = tid; idx < k * 2 * NB; idx += T) {
-		int s = idx / (2 * NB), t = idx % (2 * NB);
-		i64 v = 0;
-		if (t < k)
-			v = S[(size_t) s_prow[s] * ld + c0 + s_pcol[t]];
-		else if (t >= NB)
-			v = (t - NB == s);
-		Mw[s][t] = v;
-	}
-	__syncthreads();
-	for (int t = 0; t < k; t++) {
-		if (tid == 0) {
-			int s = t;
-			while (Mw[s][t] == 0)
-				s++;                         /* M is invertible: a non-zero entry exists below */
-			s_min = s;
-		}
-		__syncthreads();
-		const int sw = s_min;
-		if (sw != t && tid < 2 * NB) {
-			i64 tmp = Mw[sw][tid];
-			Mw[sw][tid] = Mw[t][tid];
-			Mw[t][tid] = tmp;
-		}
-		__syncthreads();
-		/* every thread takes its operands (the multiplier column t and the pivot row t are rewritten below) */
-		i64 l0 = 0, l1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-		const i64 d = Mw[t][t];
-		const int idx0 = tid, idx1 = tid + T;
-		const int sa = idx0 / (2 * NB), ca = idx0 % (2 * NB), sb2 = idx1 / (2 * NB), cb = idx1 % (2 * NB);
-		const bool doa = idx0 < k * 2 * NB && sa != t, dob = idx1 < k * 2 * NB && sb2 != t;
-		if (doa) {
-			l0 = Mw[sa][t];
-			x0 = Mw[sa][ca];
-			y0 = Mw[t][ca];
-		}
-		if (dob) {
-			l1 = Mw[sb2][t];
-			x1 = Mw[sb2][cb];
-			y1 = Mw[t][cb];
-		}
-		__syncthreads();
-		if (doa && l0 != 0)
-			Mw[sa][ca] = (ca == t) ? 0 : (i64) zp_reduce(d * x0 - l0 * y0, F);
-		if (dob && l1 != 0)
-			Mw[sb2][cb] = (cb == t) ? 0 : (i64) zp_reduce(d * x1 - l1 * y1, F);
-		__syncthreads();
-	}
-	/* scale row s by the inverse of its diagonal entry */
 	__shared__ i32 s_dinv[NB];
-	if (tid < k)
-		s_dinv[tid] = zp_inverse((i32) Mw[tid][tid], F);
-	__syncthreads();
-	for (int idx = tid; idx < k * NB; idx += T) {
-		int s = idx / NB, c = idx % NB;
-		Mw[s][NB + c] = zp_mul((i32) Mw[s][NB + c], s_dinv[s], F);
-	}
-	__syncthreads();
+	panel_invert_and_publish(S, ld, c0, k, r0, s_prow, s_pcol, Mw, s_dinv, &s_min, rowstate, rank_dev, pivcol_out, info, F);
+}
 
-	/* --- hand M^-1 to the multiplier kernel (the n x k x k product is spread over the whole GPU) */
-	for (int idx = tid; idx < NB * NB; idx += T) {
-		int s = idx / NB, t = idx % NB;
-		info->Minv[s][t] = (s < k && t < k) ? (i32) Mw[s][NB + t] : 0;
+/*
+ * The same panel factorisation on a thread-block CLUSTER: the rows of the panel are spread over PC_CTAS CTAs (8 SMs),
+ * each keeping its slice in shared memory.  Per column: every CTA proposes its first eligible row with a remote
+ * atomicMin on a slot in CTA 0's shared memory (DSMEM), ONE cluster barrier, everybody reads the winner, copies the
+ * pivot row (32 values) from its owner's shared memory and updates its own rows.  Three rotating slots let CTA 0
+ * reset a slot two steps before it is reused, so no second barrier is needed.  The single-CTA kernel spends ~100 us
+ * of its ~170 us in these 32 update steps (one SM, 57 % issue-active); here a step is about a microsecond.
+ */
+#define PC_CTAS 8
+#define PC_THREADS 256
+
+__global__ void __cluster_dims__(PC_CTAS, 1, 1) __launch_bounds__(PC_THREADS)
+k_rref_panel_cluster(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowstate, int *rank_dev, int *pivcol_out,
+                     PanelInfo *info, int chunk, Zp F)
+{
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	const int crank = (int) cluster.block_rank();
+	extern __shared__ unsigned char dyn[];
+	i32 *Pw = (i32 *) dyn;                                                   /* chunk x PSTRIDE */
+	unsigned char *taken = dyn + (size_t) chunk * PSTRIDE * sizeof(i32);    /* chunk */
+	__shared__ int s_slot[3];          /* used in CTA 0 only: winner of a step */
+	__shared__ int s_k, s_local, s_sw;
+	__shared__ int s_prow[NB], s_pcol[NB];
+	__shared__ i32 s_piv[NB], s_dinv[NB];
+	__shared__ i64 Mw[NB][2 * NB + 1];
+	const int tid = threadIdx.x, T = blockDim.x;
+	const int r0 = *rank_dev;
+	if (r0 >= n || c0 >= m) {          /* same decision in every CTA of the cluster */
+		if (crank == 0 && tid == 0)
+			info->k = 0;
+		return;
 	}
-	if (tid < k) {
-		info->prow[tid] = s_prow[tid];
-		info->pcol[tid] = s_pcol[tid];
-		rowstate[s_prow[tid]] = r0 + tid;
-		pivcol_out[r0 + tid] = c0 + s_pcol[tid];
+	const int nbw = min(NB, m - c0);
+	const int row_lo = crank * chunk, nloc = max(0, min(n, row_lo + chunk) - row_lo);
+	for (int idx = tid; idx < nloc * NB; idx += T) {
+		int i = idx / NB, c = idx % NB;
+		Pw[i * PSTRIDE + c] = (c < nbw) ? S[(size_t) (row_lo + i) * ld + c0 + c] : 0;
+	}
+	for (int i = tid; i < nloc; i += T)
+		taken[i] = rowstate[row_lo + i] >= 0;
+	if (tid == 0) {
+		s_k = 0;
+		s_slot[0] = s_slot[1] = s_slot[2] = 0x7fffffff;
 	}
 	__syncthreads();
+	cluster.sync();                    /* every CTA's shared memory is ready before the first remote access */
+	int *slot0 = cluster.map_shared_rank(s_slot, 0);
+
+	for (int c = 0; c < nbw; c++) {
+		if (s_k + r0 >= n)             /* s_k evolves identically in every CTA */
+			break;
+		if (tid == 0)
+			s_local = 0x7fffffff;
+		__syncthreads();
+		for (int i = tid; i < nloc; i += T)
+			if (!taken[i] && Pw[i * PSTRIDE + c] != 0) {
+				atomicMin(&s_local, row_lo + i);
+				break;
+			}
+		__syncthreads();
+		if (tid == 0) {
+			if (s_local != 0x7fffffff)
+				atomicMin(&slot0[c % 3], s_local);
+			if (crank == 0)
+				s_slot[(c + 1) % 3] = 0x7fffffff;      /* last read during step c - 2: every CTA is past it */
+		}
+		cluster.sync();
+		const int piv = *((volatile int *) &slot0[c % 3]);
+		if (piv == 0x7fffffff)
+			continue;
+		const int owner = piv / chunk;
+		const i32 *prow_remote = cluster.map_shared_rank(Pw, owner) + (size_t) (piv - owner * chunk) * PSTRIDE;
+		if (tid < NB)
+			s_piv[tid] = prow_remote[tid];
+		if (tid == 0) {
+			s_prow[s_k] = piv;
+			s_pcol[s_k] = c;
+			s_k += 1;
+			if (owner == crank)
+				taken[piv - row_lo] = 1;
+		}
+		__syncthreads();
+		/* fraction-free elimination of column c from the local rows, two threads per row (column c itself is never
+		 * read again and is left as it is) */
+		const i64 d = s_piv[c];
+		const int count = nbw - c - 1, h0 = (count + 1) / 2;
+		for (int idx = tid; idx < 2 * nloc; idx += T) {
+			const int i = idx >> 1, half = idx & 1;
+			if (taken[i])
+				continue;
+			const i64 l = Pw[i * PSTRIDE + c];
+			if (l == 0)
+				continue;
+			const int lo = c + 1 + (half ? h0 : 0), hi = half ? nbw : c + 1 + h0;
+			for (int cc = lo; cc < hi; cc++)
+				Pw[i * PSTRIDE + cc] = zp_reduce(d * Pw[i * PSTRIDE + cc] - l * s_piv[cc], F);
+		}
+		__syncthreads();
+	}
+	__syncthreads();
+	const int k = s_k;
+	cluster.sync();                    /* nobody reads a neighbour's shared memory after this point */
+	if (crank != 0)
+		return;
 	if (tid == 0)
-		*rank_dev = r0 + k;
+		info->k = k;
+	if (k == 0)
+		return;
+	panel_invert_and_publish(S, ld, c0, k, r0, s_prow, s_pcol, Mw, s_dinv, &s_sw, rowstate, rank_dev, pivcol_out, info, F);
 }
 
 /* W[i][t] = sum_s S[i][c0 + pcol[s]] * Minv[s][t]   (rows of the panel's own pivots: (s == t) - Minv[s][t]); one thread per (i, t) */
@@ -408,10 +531,20 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 	DevBuf<i32> scratch(use_smem ? 1 : ((size_t) n * PSTRIDE + (size_t) n / 4 + 8));
 	if (use_smem)      /* static + dynamic shared memory may exceed the 48 KB default: always opt in */
 		CUDA_CHECK(cudaFuncSetAttribute(k_rref_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) need));
+	/* panels with enough rows are factorised by a cluster of 8 CTAs (SPASM_B200_PANEL_SINGLE=1 keeps the single CTA) */
+	static const bool single = getenv("SPASM_B200_PANEL_SINGLE") != NULL;
+	const int chunk = (n + PC_CTAS - 1) / PC_CTAS;
+	const size_t cluster_smem = (size_t) chunk * PSTRIDE * sizeof(i32) + (size_t) chunk + 16;
+	const bool use_cluster = !single && n >= 256 && cluster_smem <= 160 * 1024;
+	if (use_cluster)
+		CUDA_CHECK(cudaFuncSetAttribute(k_rref_panel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cluster_smem));
 	int panels = 0;
 	for (int c0 = 0; c0 < m; c0 += NB) {
 		int width = m - c0;
-		k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, W.ptr, info.ptr, scratch.ptr, use_smem, F);
+		if (use_cluster)
+			k_rref_panel_cluster<<<PC_CTAS, PC_THREADS, cluster_smem, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, info.ptr, chunk, F);
+		else
+			k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, W.ptr, info.ptr, scratch.ptr, use_smem, F);
 		k_rref_multipliers<<<std::min(cdiv(n, 8), 148u * 4), 256, 0, s>>>(S, ld, n, c0, info.ptr, W.ptr, F);
 		dim3 g(cdiv(width, 256), NB);
 		k_copy_pivot_rows<<<g, 256, 0, s>>>(S, ld, c0, width, info.ptr, P.ptr, m);
