@@ -48,7 +48,7 @@ Stats &stats();
  * made the download of a 2.4 GB echelon form cost more than its computation.  download_bulk asks for huge pages on
  * the destination, copies chunk by chunk into pinned staging buffers and lets several host threads move each chunk
  * to its place (they take the page faults in parallel) while the next chunk is in flight. */
-size_t bulk_download_threshold();      /* 16 MB; SPASM_B200_BULK_MB overrides (read at every call: the tests toggle it) */
+size_t bulk_download_threshold();      /* 2 MB; SPASM_B200_BULK_MB overrides (read at every call: the tests toggle it) */
 void download_bulk(void *host, const void *dev, size_t bytes);
 
 /* -------------------------------------------------------------------- device buffers */

@@ -74,7 +74,7 @@ static void parallel_memcpy(char *dst, const char *src, size_t bytes, int nthrea
 size_t bulk_download_threshold()
 {
 	const char *e = getenv("SPASM_B200_BULK_MB");
-	return e ? (size_t) (atof(e) * 1048576.0) : ((size_t) 16 << 20);
+	return e ? (size_t) (atof(e) * 1048576.0) : ((size_t) 2 << 20);
 }
 
 void download_bulk(void *host, const void *dev, size_t bytes)

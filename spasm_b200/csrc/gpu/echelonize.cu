@@ -369,10 +369,10 @@ static bool rand_rewind_works()
 
 struct AheadBlock { int Sn, n, w; };          /* predicted shape of a low-rank block */
 
-/* The dense blocks (reduced by the structural pivots) of several predicted low-rank blocks, stacked in `out`
- * (block b starts at row offset[b]).  rand() is left untouched (peek). */
-static void randomized_blocks_ahead(Engine &E, const DevCsr &A, const int *p, const std::vector<AheadBlock> &plan,
-                                    DevBuf<i32> &out, int &ldB, std::vector<int> &offset)
+/* Row choices and coefficients of several predicted low-rank blocks, as the reference will draw them; rand() is left
+ * untouched (peek: state snapshot, then rewound).  Block b starts at row offset[b] of the stacked list. */
+static size_t peek_combinations(Engine &E, const int *p, const std::vector<AheadBlock> &plan, DevBuf<int> &d_rows, DevBuf<i32> &d_coef,
+                                std::vector<int> &offset)
 {
 	cudaStream_t s = ctx().stream;
 	RandSnapshot snap;
@@ -385,7 +385,7 @@ static void randomized_blocks_ahead(Engine &E, const DevCsr &A, const int *p, co
 		total += b.Sn;
 	}
 	std::vector<int> rows(total * w);
-	DevBuf<i32> d_coef(total * w);
+	d_coef.alloc(total * w);
 	size_t at = 0;
 	for (const AheadBlock &b : plan) {
 		for (int k = 0; k < b.Sn; k++)
@@ -395,14 +395,149 @@ static void randomized_blocks_ahead(Engine &E, const DevCsr &A, const int *p, co
 		at += b.Sn;
 	}
 	rand_restore(snap);
+	d_rows.upload(rows.data(), rows.size(), s);
+	sync();                              /* `rows` is a local */
+	stats().pub.h2d_bytes += (i64) rows.size() * 4;
+	return total;
+}
+
+/* The dense blocks (reduced by the structural pivots) of several predicted low-rank blocks, stacked in `out`. */
+static void randomized_blocks_ahead(Engine &E, const DevCsr &A, const int *p, const std::vector<AheadBlock> &plan,
+                                    DevBuf<i32> &out, int &ldB, std::vector<int> &offset)
+{
+	DevBuf<int> d_rows;
+	DevBuf<i32> d_coef;
+	size_t total = peek_combinations(E, p, plan, d_rows, d_coef, offset);
+	E.block_from_combos(A, d_rows.ptr, d_coef.ptr, (int) total, plan[0].w, out, ldB);
+}
+
+/* blocks the low-rank finisher will most likely process next (every block has full rank and keeps the weight) */
+static std::vector<AheadBlock> plan_lowrank(int n, int rank_ub, int w, const struct echelonize_opts *opts)
+{
+	std::vector<AheadBlock> plan;
+	int n2 = n, ub2 = rank_ub;
+	size_t rows_ahead = 0;
+	const size_t row_budget = (size_t) 8 * opts->dense_block_size;
+	while (ub2 > 0 && rows_ahead < row_budget && (size_t) (plan.size() + 1) * w * opts->dense_block_size < ((size_t) 1 << 28)) {
+		int sn2 = spasm_min(ub2, opts->dense_block_size);
+		plan.push_back({sn2, n2, w});
+		rows_ahead += sn2;
+		n2 -= sn2;
+		ub2 -= sn2;
+	}
+	return plan;
+}
+
+/* rows of the Schur complement solved in one batch by the dense finisher (bounded by the memory of the stacked blocks) */
+static int dense_rows_ahead(int Sm0, int remaining, int Sn, const struct echelonize_opts *opts, bool no_ahead)
+{
+	size_t per_row = (size_t) std::max((Sm0 + 3) & ~3, 4) * sizeof(i32);
+	size_t max_rows = std::max<size_t>((size_t) Sn, ((size_t) 12 << 30) / per_row);
+	int take = no_ahead ? Sn : (int) std::min<size_t>((size_t) remaining, max_rows);
+	return std::max(Sn, take - take % opts->dense_block_size);
+}
+
+/*
+ * Speculation across the density estimate.  A pass over the pivot DAG costs its depth, not its width, and the density
+ * estimate (100 rows) is a full pass of its own.  When the finisher that will run if the Schur complement turns out
+ * dense is known beforehand (it only depends on the aspect ratio and on the options), its first batch of right-hand
+ * sides is solved IN THE SAME PASS as the 100 sampled rows.  If the estimate says "sparse" the extra columns are
+ * thrown away.  The rand() draws happen in the reference's order: 100 for the estimate, then the blocks' draws are
+ * peeked (and consumed for real when the blocks are processed).
+ */
+struct Speculation {
+	bool valid = false;
+	int kind = 0;                      /* 1 = low-rank blocks, 2 = dense blocks */
+	int n = 0, w = 0;                  /* what the finisher must start with for the batch to be usable */
+	std::vector<AheadBlock> plan;      /* kind 1 */
+	std::vector<int> offset;
+	int take = 0;                      /* kind 2: rows p[0:take] */
+	DevBuf<i32> B;
+	int ldB = 0;
+	bool froze_columns = false;        /* begin_dense() was called for this batch */
+	void discard(Engine &E)
+	{
+		if (froze_columns)
+			E.dense_ready = false;
+		valid = false;
+		froze_columns = false;
+		B.release();
+	}
+};
+
+/* reference: src/spasm_schur.c:11-44 (density) + the first batch of the predicted finisher */
+static double estimate_density_speculative(Engine &E, const DevCsr &A, const int *p, int n, int R, const struct echelonize_opts *opts, Speculation &spec)
+{
+	static const bool off = getenv("SPASM_B200_NO_SPECULATION") != NULL || getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
+	spec.valid = false;
+	const int Sm = E.m - E.U.n;
+	if (off || n == 0 || Sm <= 0 || comm_world() > 1 || E.dense_ready)
+		return estimate_density(E, A, p, n, R);
+	cudaStream_t s = ctx().stream;
+	/* 1. the estimate's own draws */
+	std::vector<int> rows(R);
+	for (int t = 0; t < R; t++)
+		rows[t] = p[rand() % n];
 	DevBuf<int> d_rows;
 	d_rows.upload(rows.data(), rows.size(), s);
-	stats().pub.h2d_bytes += (i64) rows.size() * 4;
-	E.block_from_combos(A, d_rows.ptr, d_coef.ptr, (int) total, w, out, ldB);
+	/* 2. which finisher, with which first batch */
+	const double aspect_ratio = (double) n / Sm;
+	DevBuf<int> d_rows2;
+	DevBuf<i32> d_coef;
+	int N = 0;
+	if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio) {
+		const int rank_ub = spasm_min(n, Sm);
+		const int w = (opts->low_rank_start_weight < 0) ? (int) ceil(-log(0.01) * n / rank_ub) : (int) opts->low_rank_start_weight;
+		if (w > 0 && rand_rewind_works()) {
+			spec.plan = plan_lowrank(n, rank_ub, w, opts);
+			if (spec.plan.size() >= 1) {
+				spec.kind = 1;
+				spec.w = w;
+				N = (int) peek_combinations(E, p, spec.plan, d_rows2, d_coef, spec.offset);
+			}
+		}
+	} else if (opts->enable_dense || opts->enable_GPLU) {
+		spec.kind = 2;
+		spec.take = N = dense_rows_ahead(Sm, n, spasm_min(opts->dense_block_size, n), opts, false);
+		d_rows2.upload(p, (size_t) N, s);
+	}
+	if (N <= 0 || R + N > panel_capacity(E.m)) {
+		spec.kind = 0;
+		sync();
+		E.solve_rows(A, d_rows.ptr, R, false);
+		i64 nnz0 = panel_count_nonzero(E.panel, E.Uqinv.ptr);
+		return ((double) nnz0) / Sm / R;
+	}
+	/* 3. one pass for both */
+	if (!E.G_ready)
+		E.rebuild_schedule();
+	GpuTimer t;
+	t.start();
+	const int R_off = (R + 3) & ~3;
+	E.panel.shape(E.m, R_off + N);
+	panel_scatter_rows(A, d_rows.ptr, R, E.panel, E.F, false);
+	if (spec.kind == 1)
+		panel_scatter_combos(A, d_rows2.ptr, d_coef.ptr, N, spec.w, E.panel, E.F, R_off);
+	else
+		panel_scatter_rows(A, d_rows2.ptr, N, E.panel, E.F, false, R_off);
+	panel_solve(E.G, E.panel.X, E.panel.ld, R_off + N, E.F);
+	stats().pub.ms_solve += t.stop_ms();
+	E.account_bytes(R_off + N);
+	i64 nnz = panel_count_nonzero(E.panel, E.Uqinv.ptr, R);
+	/* 4. the finisher's batch as a dense block over the columns that are not pivotal now */
+	E.begin_dense();
+	spec.froze_columns = true;
+	spec.ldB = std::max((E.Sm0 + 3) & ~3, 4);
+	spec.B.ensure((size_t) N * spec.ldB);
+	panel_gather_dense(E.panel, E.d_q0.ptr, E.Sm0, spec.B.ptr, spec.ldB, R_off, N);
+	spec.n = n;
+	spec.valid = true;
+	sync();
+	return ((double) nnz) / Sm / R;
 }
 
 /* reference: src/spasm_echelonize.c:315-379 */
-static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts, Speculation *spec = nullptr)
 {
 	E.begin_dense();
 	int Sm = E.m - E.rank();
@@ -415,6 +550,14 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 	size_t next_ahead = 0;
 	int ahead_ld = 0;
 	static const bool no_ahead = getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
+	if (spec && spec->valid && spec->kind == 1 && spec->n == n && spec->w == w) {
+		/* the first blocks were solved together with the density estimate */
+		plan = spec->plan;
+		ahead_offset = spec->offset;
+		ahead = std::move(spec->B);
+		ahead_ld = spec->ldB;
+		spec->valid = false;
+	}
 	int round = 0;
 	for (;;) {
 		int Sn = spasm_min(rank_ub, opts->dense_block_size);
@@ -433,19 +576,8 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 		} else {
 			plan.clear();
 			next_ahead = 0;
-			if (w > 0 && !no_ahead && rand_rewind_works()) {
-				/* predict: every block has full rank and keeps the weight */
-				int n2 = n, ub2 = rank_ub;
-				size_t rows_ahead = 0;
-				const size_t row_budget = (size_t) 8 * opts->dense_block_size;
-				while (ub2 > 0 && rows_ahead < row_budget && (size_t) (plan.size() + 1) * w * opts->dense_block_size < ((size_t) 1 << 28)) {
-					int sn2 = spasm_min(ub2, opts->dense_block_size);
-					plan.push_back({sn2, n2, w});
-					rows_ahead += sn2;
-					n2 -= sn2;
-					ub2 -= sn2;
-				}
-			}
+			if (w > 0 && !no_ahead && rand_rewind_works())
+				plan = plan_lowrank(n, rank_ub, w, opts);      /* predict: every block has full rank and keeps the weight */
 			if (plan.size() > 1) {
 				randomized_blocks_ahead(E, A, p, plan, ahead, ahead_ld, ahead_offset);
 				for (i64 t = 0; t < (i64) Sn * w; t++)
@@ -481,7 +613,7 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 }
 
 /* reference: src/spasm_echelonize.c:385-463 */
-static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts, Speculation *spec = nullptr)
 {
 	E.begin_dense();
 	cudaStream_t s = ctx().stream;
@@ -495,17 +627,22 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 	const int base = processed;
 	const int *p0 = p;
 	static const bool no_ahead = getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
+	if (spec && spec->valid && spec->kind == 2 && spec->n == n && spec->take > 0) {
+		/* the first batch was solved together with the density estimate */
+		B = std::move(spec->B);
+		ldB = spec->ldB;
+		ahead_begin = 0;
+		ahead_end = spec->take;
+		spec->valid = false;
+	}
 	for (;;) {
 		int Sn = spasm_min(opts->dense_block_size, n - processed);
 		if (Sn <= 0)
 			break;
 		LOG("[echelonize/dense] Round %d. processing S[%d:%d] (%d x %d)\n", round, processed, processed + Sn, Sn, Sm);
 		if (processed >= ahead_end) {
-			/* structural solves of the next blocks in one batch (bounded by the memory of the stacked blocks) */
-			size_t per_row = (size_t) std::max((E.Sm0 + 3) & ~3, 4) * sizeof(i32);
-			size_t max_rows = std::max<size_t>((size_t) Sn, ((size_t) 12 << 30) / per_row);
-			int take = no_ahead ? Sn : (int) std::min<size_t>((size_t) (n - processed), max_rows);
-			take = std::max(Sn, take - take % opts->dense_block_size);
+			/* structural solves of the next blocks in one batch */
+			int take = dense_rows_ahead(E.Sm0, n - processed, Sn, opts, no_ahead);
 			DevBuf<int> d_rows;
 			d_rows.upload(p0 + (processed - base), (size_t) take, s);
 			E.block_from_rows(A, d_rows.ptr, take, B, ldB);
@@ -621,10 +758,22 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 	if (opts->dense_block_size <= 0)
 		errx(1, "[spasm-b200] dense_block_size must be positive");
 
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace] core/%-23s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	E.init(m, dA0.prime);
+	lap("init");
 	DevCsr dS;                       /* current Schur complement once a round has run */
 	const DevCsr *cur = &dA0;
 
+	Speculation spec;
 	std::vector<int> p((size_t) std::max(n, 1));
 	std::vector<int> p_in;           /* empty = identity */
 	double density = (double) dA0.nnz / n / m;
@@ -637,6 +786,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 		}
 		LOG("[echelonize] round %d\n", round);
 		npiv = extract_structural(E, *cur, p_in.empty() ? NULL : p_in.data(), p.data(), opts->enable_greedy_pivot_search, round);
+		lap("extract_structural");
 		st.pub.nrounds = round + 1;
 		st.pair_start.push_back((int) st.pair_row.size());
 		if (npiv < opts->min_pivot_proportion * spasm_min(n, m - E.U.n)) {
@@ -644,7 +794,8 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			status = 2;
 			break;
 		}
-		density = estimate_density(E, *cur, p.data() + npiv, n - npiv, 100);
+		density = estimate_density_speculative(E, *cur, p.data() + npiv, n - npiv, 100, opts, spec);
+		lap("estimate_density");
 		if (round < 64)
 			st.pub.density[round] = density;
 		if (density > opts->sparsity_threshold) {
@@ -652,9 +803,11 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			status = 2;
 			break;
 		}
+		spec.discard(E);                 /* sparse after all: the finisher's batch is not needed */
 		LOG("Schur complement is %d x %d, estimated density : %.2f\n", n - npiv, m - E.U.n, density);
 		DevCsr S;
 		schur_sparse(E, *cur, p.data() + npiv, n - npiv, S);
+		lap("schur_sparse");
 		std::vector<int> p_out((size_t) (n - npiv));
 		for (int k = 0; k < n - npiv; k++) {
 			int row = p[npiv + k];
@@ -684,10 +837,10 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 		LOG("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
 		if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio) {
 			st.pub.finish = 1;
-			finish_lowrank(E, *cur, p.data() + npiv, n - npiv, opts);
+			finish_lowrank(E, *cur, p.data() + npiv, n - npiv, opts, &spec);
 		} else if (opts->enable_dense && density > opts->sparsity_threshold) {
 			st.pub.finish = 2;
-			finish_dense(E, *cur, p.data() + npiv, n - npiv, opts);
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, opts, &spec);
 		} else if (opts->enable_GPLU) {
 			/* The reference finishes row by row (echelonize_GPLU, echelonize.c:54-187): leftmost pivot of each
 			 * reduced row.  That rule selects the column rank profile of the Schur complement, which is what
@@ -697,10 +850,11 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			st.pub.finish = 3;
 			struct echelonize_opts o2 = *opts;
 			o2.enable_tall_and_skinny = 0;
-			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2);
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2, &spec);
 		} else {
 			LOG("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
 		}
+		lap("finish");
 	}
 }
 

@@ -49,11 +49,11 @@ __global__ void k_scatter_rows(int R, const int *__restrict__ rows, const i64 *_
 	}
 }
 
-void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first)
+void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first, int r_off)
 {
 	if (R == 0)
 		return;
-	k_scatter_rows<<<std::min(cdiv((size_t) R * 32, 256), 148u * 16), 256, 0, ctx().stream>>>(R, d_rows, B.p, B.j, B.x, P.X, P.ld, F, skip_first ? 1 : 0,
+	k_scatter_rows<<<std::min(cdiv((size_t) R * 32, 256), 148u * 16), 256, 0, ctx().stream>>>(R, d_rows, B.p, B.j, B.x, P.X + r_off, P.ld, F, skip_first ? 1 : 0,
 	                                                                                             P.masked ? P.mask.ptr : nullptr, P.mw);
 	LAUNCHED(1);
 	KERNEL_CHECK();
@@ -74,12 +74,12 @@ __global__ void k_scatter_combos(i64 total, int w, const int *__restrict__ rows,
 	}
 }
 
-void panel_scatter_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, Panel &P, const Zp &F)
+void panel_scatter_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, Panel &P, const Zp &F, int r_off)
 {
 	i64 total = (i64) N * w;
 	if (total == 0)
 		return;
-	k_scatter_combos<<<std::min(cdiv((size_t) total, 256), 148u * 32), 256, 0, ctx().stream>>>(total, w, d_rows, d_coef, A.p, A.j, A.x, P.X, P.ld, F);
+	k_scatter_combos<<<std::min(cdiv((size_t) total, 256), 148u * 32), 256, 0, ctx().stream>>>(total, w, d_rows, d_coef, A.p, A.j, A.x, P.X + r_off, P.ld, F);
 	LAUNCHED(1);
 	KERNEL_CHECK();
 }
@@ -126,12 +126,13 @@ __global__ void k_gather_dense(int R, int Sm, const int *__restrict__ q, const i
 	}
 }
 
-void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS)
+void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS, int r_off, int count)
 {
-	if (P.R == 0 || Sm == 0)
+	const int R = count < 0 ? P.R - r_off : count;
+	if (R <= 0 || Sm == 0)
 		return;
-	dim3 grid(cdiv(Sm, 32), cdiv(P.R, 32)), block(32, 8);
-	k_gather_dense<<<grid, block, 0, ctx().stream>>>(P.R, Sm, d_q, P.X, P.ld, S, ldS);
+	dim3 grid(cdiv(Sm, 32), cdiv(R, 32)), block(32, 8);
+	k_gather_dense<<<grid, block, 0, ctx().stream>>>(R, Sm, d_q, P.X + r_off, P.ld, S, ldS);
 	LAUNCHED(1);
 	KERNEL_CHECK();
 }
@@ -206,21 +207,22 @@ __global__ void k_sum_i64(int n, const i64 *__restrict__ v, unsigned long long *
 		atomicAdd(out, acc);
 }
 
-i64 panel_count_nonzero(const Panel &P, const int *d_flag)
+i64 panel_count_nonzero(const Panel &P, const int *d_flag, int R_limit)
 {
-	if (P.R == 0 || P.nnodes == 0)
+	const int R = R_limit < 0 ? P.R : std::min(P.R, R_limit);
+	if (R == 0 || P.nnodes == 0)
 		return 0;
 	cudaStream_t s = ctx().stream;
 	int nchunks = cdiv(P.nnodes, CHUNK);
-	DevBuf<int> part((size_t) nchunks * P.R);
-	DevBuf<i64> rowlen((size_t) P.R);
+	DevBuf<int> part((size_t) nchunks * R);
+	DevBuf<i64> rowlen((size_t) R);
 	DevBuf<unsigned long long> total(1);
 	total.zero(s);
-	dim3 grid(cdiv(P.R, 128), nchunks);
-	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, P.R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0,
+	dim3 grid(cdiv(R, 128), nchunks);
+	k_panel_sparse<false><<<grid, 128, 0, s>>>(P.nnodes, R, P.X, P.ld, d_flag, part.ptr, nullptr, nullptr, nullptr, nullptr, 0,
 	                                           P.masked ? P.mask.ptr : nullptr, P.mw);
-	k_chunk_prefix<<<cdiv(P.R, 128), 128, 0, s>>>(nchunks, P.R, part.ptr, rowlen.ptr, 0);
-	k_sum_i64<<<std::min(cdiv(P.R, 256), 64u), 256, 0, s>>>(P.R, rowlen.ptr, total.ptr);
+	k_chunk_prefix<<<cdiv(R, 128), 128, 0, s>>>(nchunks, R, part.ptr, rowlen.ptr, 0);
+	k_sum_i64<<<std::min(cdiv(R, 256), 64u), 256, 0, s>>>(R, rowlen.ptr, total.ptr);
 	LAUNCHED(3);
 	KERNEL_CHECK();
 	return (i64) fetch(total.ptr);

@@ -29,16 +29,16 @@ struct Panel {
 int panel_capacity(int nnodes, double gb = 16.0);
 
 /* X[B.j[e]][r] += B.x[e] for every entry e of row rows[r] (r < R); skip_first drops the first entry of each row */
-void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first);
+void panel_scatter_rows(const DevCsr &B, const int *d_rows, int R, Panel &P, const Zp &F, bool skip_first, int r_off = 0);
 /* X[.][k] += coef[k*w+t] * A[rows[k*w+t]]   for k < N, t < w */
-void panel_scatter_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, Panel &P, const Zp &F);
+void panel_scatter_combos(const DevCsr &A, const int *d_rows, const i32 *d_coef, int N, int w, Panel &P, const Zp &F, int r_off = 0);
 /* transposed variant for spasm_kernel: right-hand side r = column cols[r] of U, i.e. X[i][r] = U[i][cols[r]] */
 void panel_scatter_columns(const DevCsr &U, const int *d_colslot /* size m: slot of a column or -1 */, Panel &P);
 
 /* S[r*ldS + c] = X[q[c]][r]  (row-major dense block, reference: src/spasm_schur.c:205-233 "gather") */
-void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS);
+void panel_gather_dense(const Panel &P, const int *d_q, int Sm, i32 *S, int ldS, int r_off = 0, int count = -1);      /* right-hand sides r_off .. r_off + count */
 /* number of non-zero entries on nodes with flag[node] < 0 (non-pivotal columns) over the whole panel */
-i64 panel_count_nonzero(const Panel &P, const int *d_flag);
+i64 panel_count_nonzero(const Panel &P, const int *d_flag, int R_limit = -1);      /* first R_limit right-hand sides only */
 
 /* CSR of the panel restricted to nodes with flag[node] < 0, entries of a row by increasing node.
  * If d_first != NULL, row r starts with the extra entry (first_col[r], first_val) (used by rref / kernel). */
