@@ -205,7 +205,7 @@ def _echelon_arrays(product, A, **kw):
 
 
 def test_staged_download_of_large_results_is_transparent(product, monkeypatch):
-    """Results above 16 MB leave the device through pinned staging buffers and several copy threads (download_bulk);
+    """Results above 2 MB leave the device through pinned staging buffers and several copy threads (download_bulk);
     forcing that path on a small result (threshold 4 KB, chunks still 32 MB) and forbidding it must give the same
     arrays, for the echelon form, the RREF and the kernel basis."""
     t = synthetic.config3(0.02)
