@@ -158,6 +158,19 @@ struct GreedyArgs {
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
 
+/* Expansion of a pivot row: its column indices are loaded 8 at a time BEFORE any of them is marked -- the marks are
+ * shared-memory atomics the compiler will not move loads across, and one L2 round trip per entry, serialised, was
+ * most of the latency of a BFS step (which is the critical path of a chain of dependent commits). */
+#define EXPAND_ROW(MARK, b, e)                                                         \
+	for (i64 k0_ = (b); k0_ < (e); k0_ += 8) {                                        \
+		int c_[8];                                                                     \
+		_Pragma("unroll") for (int u_ = 0; u_ < 8; u_++)                               \
+			c_[u_] = (k0_ + u_ < (e)) ? __ldg(&a.Aj[k0_ + u_]) : -1;                   \
+		_Pragma("unroll") for (int u_ = 0; u_ < 8; u_++)                               \
+			if (c_[u_] >= 0)                                                           \
+				MARK(c_[u_], vis, srv, queue, &sh);                                    \
+	}
+
 struct GreedyShared {
 	int row, head, tail, alive, npiv_local, scan, replayed, np_now, turn;
 };
@@ -258,8 +271,7 @@ __global__ void __launch_bounds__(256, 8) k_greedy(GreedyArgs a)
 					int I = ld_volatile(&a.qinv[j]);
 					if (I >= 0) {
 						i64 b = a.Ap[I], e = a.Ap[I + 1];
-						for (i64 k = b; k < e; k++)
-							greedy_mark(a.Aj[k], vis, srv, queue, &sh);
+						EXPAND_ROW(greedy_mark, b, e)
 						my_edges += (unsigned long long) (e - b);
 					}
 				}
@@ -305,8 +317,7 @@ __global__ void __launch_bounds__(256, 8) k_greedy(GreedyArgs a)
 				} else if (vis[word] & bit) {   /* a reached column became pivotal: expand its row */
 					int I = ld_volatile(&a.qinv[j]);
 					i64 b = a.Ap[I], e = a.Ap[I + 1];
-					for (i64 k = b; k < e; k++)
-						greedy_mark(a.Aj[k], vis, srv, queue, &sh);
+					EXPAND_ROW(greedy_mark, b, e)
 					my_edges += (unsigned long long) (e - b);
 				}
 			}
@@ -509,8 +520,7 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 					int I = visible_owner(a.qinv, j, i);
 					if (I >= 0) {
 						i64 b = a.Ap[I], e = a.Ap[I + 1];
-						for (i64 k = b; k < e; k++)
-							ooo_mark(a.Aj[k], vis, srv, queue, &sh);
+						EXPAND_ROW(ooo_mark, b, e)
 						my_edges += (unsigned long long) (e - b);
 					}
 				}
@@ -558,8 +568,7 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 						}
 					} else if (vis[word] & bit) {   /* a reached column became pivotal: expand its row */
 						i64 b = a.Ap[owner], e = a.Ap[owner + 1];
-						for (i64 k = b; k < e; k++)
-							ooo_mark(a.Aj[k], vis, srv, queue, &sh);
+						EXPAND_ROW(ooo_mark, b, e)
 						my_edges += (unsigned long long) (e - b);
 					}
 				}
