@@ -404,9 +404,11 @@ struct GreedyOooArgs {
 	unsigned long long *edges;
 };
 
+#define ROWC_MAX 128
 struct GreedyOooShared {
 	int row, head, tail, alive, npiv_local, np_now, scan, blocked, npend, changed;
 	int pend[PEND_CAP];
+	int rowc[ROWC_MAX];      /* column indices of the current row when it has at most ROWC_MAX entries */
 };
 
 /* row owning the pivot of column j as seen by row i, or -1 */
@@ -471,39 +473,60 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 		const i64 rb = a.Ap[i], re = a.Ap[i + 1];
 		int *mysurv = a.surv + (size_t) i * SURV_SLOTS;
 
-		/* ---- scatter the row (pivots.c:198-215) and publish its candidate columns */
-		if (tid == 0) {
-			int np = ld_volatile(a.npiv);
+		/* ---- scatter the row (pivots.c:198-215) and publish its candidate columns.  Warp 0: the lanes fetch the
+		 * entries and their owners in parallel (two round trips for the whole row instead of two per entry), lane 0
+		 * consumes them in row order.  Short rows are also kept in shared memory for the commit and the reset. */
+		if (tid < 32) {
+			int np = 0;
+			if (tid == 0) {
+				np = ld_volatile(a.npiv);
+				__threadfence();
+				sh.npiv_local = np;
+			}
+			np = __shfl_sync(0xffffffffu, np, 0);      /* the owners below are read after the journal length */
 			__threadfence();
-			sh.npiv_local = np;
+			const bool cache_row = (re - rb) <= ROWC_MAX;
 			int tail = 0, alive = 0;
-			for (i64 k = rb; k < re; k++) {
-				int j = a.Aj[k];
-				unsigned bit = 1u << (j & 31);
-				int word = j >> 5;
-				if ((vis[word] | srv[word]) & bit)
-					continue;                   /* repeated column */
-				if (visible_owner(a.qinv, j, i) < 0) {
-					srv[word] |= bit;
-					if (alive < SURV_SLOTS)
-						mysurv[alive] = j;
-					alive += 1;
-				} else {
-					queue[tail++] = j;
-					vis[word] |= bit;
+			for (i64 k0 = rb; k0 < re; k0 += 32) {
+				const i64 k = k0 + tid;
+				const int jmine = (k < re) ? a.Aj[k] : -1;
+				const int omine = (jmine >= 0) ? visible_owner(a.qinv, jmine, i) : -1;
+				if (cache_row && k < re)
+					sh.rowc[k - rb] = jmine;
+				const int cnt = (int) min((i64) 32, re - k0);
+				for (int u = 0; u < cnt; u++) {
+					const int j = __shfl_sync(0xffffffffu, jmine, u);
+					const int own = __shfl_sync(0xffffffffu, omine, u);
+					if (tid != 0)
+						continue;
+					unsigned bit = 1u << (j & 31);
+					int word = j >> 5;
+					if ((vis[word] | srv[word]) & bit)
+						continue;               /* repeated column */
+					if (own < 0) {
+						srv[word] |= bit;
+						if (alive < SURV_SLOTS)
+							mysurv[alive] = j;
+						alive += 1;
+					} else {
+						queue[tail++] = j;
+						vis[word] |= bit;
+					}
 				}
 			}
-			for (int t = alive; t < SURV_SLOTS; t++)
-				mysurv[t] = -1;
-			if (alive > SURV_SLOTS)
-				mysurv[0] = -2;                 /* too many to list: blocks the rows above until resolved */
-			__threadfence();
-			*((volatile int *) &a.status[i]) = 1;
-			sh.head = 0;
-			sh.tail = tail;
-			sh.alive = alive;
-			sh.npend = -1;                      /* pending list not built yet */
-			sh.changed = 0;
+			if (tid == 0) {
+				for (int t = alive; t < SURV_SLOTS; t++)
+					mysurv[t] = -1;
+				if (alive > SURV_SLOTS)
+					mysurv[0] = -2;             /* too many to list: blocks the rows above until resolved */
+				__threadfence();
+				*((volatile int *) &a.status[i]) = 1;
+				sh.head = 0;
+				sh.tail = tail;
+				sh.alive = alive;
+				sh.npend = -1;                  /* pending list not built yet */
+				sh.changed = 0;
+			}
 		}
 		__syncthreads();
 
@@ -620,9 +643,17 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 				}
 				bool conflict = (st == 0);      /* candidates not published yet: unknown */
 				if (!conflict) {
+					/* the 8 slots in two 16-byte loads (one round trip; the slots are independent words, a list
+					 * that shrinks between the two halves is still a superset of the final one) */
 					const int *rs = a.surv + (size_t) r * SURV_SLOTS;
-					for (int q = 0; q < SURV_SLOTS && !conflict; q++) {
-						int c = ld_volatile(&rs[q]);
+					int cand[SURV_SLOTS];
+					asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+					             : "=r"(cand[0]), "=r"(cand[1]), "=r"(cand[2]), "=r"(cand[3]) : "l"(rs) : "memory");
+					asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+					             : "=r"(cand[4]), "=r"(cand[5]), "=r"(cand[6]), "=r"(cand[7]) : "l"(rs + 4) : "memory");
+#pragma unroll
+					for (int q = 0; q < SURV_SLOTS; q++) {
+						const int c = cand[q];
 						if (c == -2)
 							conflict = true;
 						else if (c >= 0 && ((vis[c >> 5] | srv[c >> 5]) & (1u << (c & 31))))
@@ -651,8 +682,9 @@ __global__ void __launch_bounds__(256, 6) k_greedy_ooo(GreedyOooArgs a)
 		if (tid == 0) {
 			if (sh.alive > 0) {
 				int j = -1;
+				const bool cached = (re - rb) <= ROWC_MAX;
 				for (i64 k = rb; k < re; k++) {     /* first survivor in row order (pivots.c:233-237) */
-					int c = a.Aj[k];
+					int c = cached ? sh.rowc[k - rb] : a.Aj[k];
 					if (srv[c >> 5] & (1u << (c & 31))) {
 						j = c;
 						break;
