@@ -59,7 +59,7 @@ def make_workload(name: str, scale: float):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe), through NVML (nvidia-smi as a fallback)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -70,6 +70,29 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
 
     def run(self):
+        # NVML in-process when available: forking nvidia-smi from a process that holds a CUDA context and GBs of mapped
+        # memory stalls the timed thread for tens of milliseconds (page-table copy under the mm lock)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()] if vis else []
+            h = pynvml.nvmlDeviceGetHandleByIndex(ids[self.index] if self.index < len(ids) else self.index)
+            flags = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = get_reasons(h)
+                for nm, bit in flags.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                self.stop_flag.wait(0.05)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -281,7 +304,7 @@ def main() -> None:
         for k, v in table.items():
             v["GBps"] = v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0
             v["frac"] = v["GBps"] / pk["hbm_gbs"]
-            v["traffic"] = traffic.get(k)
+            v["traffic"] = traffic.get(k, traffic.get(k + "_per_launch"))      # dram bytes of one launch (one per step for these kernels)
         dominant = max(table, key=lambda k: table[k]["ms"])
         d = table[dominant]
         kernels = {k: v["ms"] for k, v in table.items()}

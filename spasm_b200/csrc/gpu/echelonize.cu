@@ -471,7 +471,9 @@ static double estimate_density_speculative(Engine &E, const DevCsr &A, const int
 	static const bool off = getenv("SPASM_B200_NO_SPECULATION") != NULL || getenv("SPASM_B200_NO_SOLVE_AHEAD") != NULL;
 	spec.valid = false;
 	const int Sm = E.m - E.U.n;
-	if (off || n == 0 || Sm <= 0 || comm_world() > 1 || E.dense_ready)
+	/* with several ranks the merged pass is replicated (it is bound by the depth of the DAG, not by its width: slicing it
+	 * would only add a collective), every rank ends up with the same block */
+	if (off || n == 0 || Sm <= 0 || E.dense_ready)
 		return estimate_density(E, A, p, n, R);
 	cudaStream_t s = ctx().stream;
 	/* 1. the estimate's own draws */
