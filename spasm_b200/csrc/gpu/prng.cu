@@ -50,29 +50,46 @@ __device__ void sha256_prng_block(uint32_t seed_lo, uint32_t seed_hi, uint32_t p
 	H[4] = 0x510e527f + e; H[5] = 0x9b05688c + f; H[6] = 0x1f83d9ab + g; H[7] = 0x5be0cd19 + h;
 }
 
-/* thread k: out[k*stride + t] = t-th output of the stream (prime, seed0 + k, seq), for t in [first, count) */
-__global__ void k_prng_streams(int N, int count, int first, uint64_t seed0, uint32_t seq, uint32_t prime, uint32_t mask, Zp F, i32 *out, int stride)
+/* warp k: out[k*stride + t] = t-th output of the stream (prime, seed0 + k, seq), t < count.  The generator is SHA-256 in
+ * counter mode with rejection sampling (reference: src/spasm_prng.c): the 32 lanes hash 32 consecutive counters at once,
+ * the accepted words are ranked with a warp prefix sum (lane order = counter order, word order inside a digest), and
+ * the first `count` of them are the stream.  One thread per stream hashed ~50 blocks in sequence: 1 ms per call on the
+ * critical path of every randomized block. */
+__global__ void k_prng_streams(int N, int count, uint64_t seed0, uint32_t seq, uint32_t prime, uint32_t mask, Zp F, i32 *out, int stride)
 {
-	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (k >= N)
 		return;
-	uint64_t seed = seed0 + (uint64_t) k;
-	uint32_t H[8];
-	uint32_t counter = 0;
-	sha256_prng_block((uint32_t) seed, (uint32_t) (seed >> 32), prime, counter++, seq, H);
-	int pos = 0;
-	for (int t = first; t < count; t++) {
-		for (;;) {
-			if (pos == 8) {
-				sha256_prng_block((uint32_t) seed, (uint32_t) (seed >> 32), prime, counter++, seq, H);
-				pos = 0;
-			}
-			uint32_t v = H[pos++] & mask;
+	const uint64_t seed = seed0 + (uint64_t) k;
+	int produced = 0;
+	uint32_t base = 0;
+	while (produced < count) {
+		uint32_t H[8];
+		sha256_prng_block((uint32_t) seed, (uint32_t) (seed >> 32), prime, base + lane, seq, H);
+		int mine = 0;
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			mine += ((H[u] & mask) < prime);
+		int pre = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			int o = __shfl_up_sync(0xffffffffu, pre, d);
+			if (lane >= d)
+				pre += o;
+		}
+		const int total = __shfl_sync(0xffffffffu, pre, 31);
+		int at = produced + pre - mine;
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const uint32_t v = H[u] & mask;
 			if (v < prime) {
-				out[(size_t) k * stride + t] = zp_reduce((i64) v, F);
-				break;
+				if (at < count)
+					out[(size_t) k * stride + at] = zp_reduce((i64) v, F);
+				at++;
 			}
 		}
+		produced += total;
+		base += 32;
 	}
 }
 
@@ -97,7 +114,7 @@ void prng_combo_coefficients(i64 prime, int N, int w, i32 *d_coef)
 	k_fill_first<<<cdiv(N, 128), 128, 0, s>>>(N, w, d_coef);
 	/* the stream of row k starts at its SECOND coefficient: slot t >= 1 receives output number t - 1 */
 	if (w > 1)
-		k_prng_streams<<<cdiv(N, 64), 64, 0, s>>>(N, w - 1, 0, 0, 0, (uint32_t) prime, (uint32_t) (pow2 - 1), F, d_coef + 1, w);
+		k_prng_streams<<<cdiv((size_t) N * 32, 128), 128, 0, s>>>(N, w - 1, 0, 0, (uint32_t) prime, (uint32_t) (pow2 - 1), F, d_coef + 1, w);
 	LAUNCHED(2);
 	KERNEL_CHECK();
 }
@@ -114,7 +131,7 @@ extern "C" void spasm_b200_prng_stream(i64 prime, u64 seed, u32 seq, int count, 
 	while (pow2 < prime)
 		pow2 <<= 1;
 	DevBuf<i32> d((size_t) std::max(count, 1));
-	k_prng_streams<<<1, 32, 0, s>>>(1, count, 0, seed, seq, (uint32_t) prime, (uint32_t) (pow2 - 1), F, d.ptr, count);
+	k_prng_streams<<<1, 32, 0, s>>>(1, count, seed, seq, (uint32_t) prime, (uint32_t) (pow2 - 1), F, d.ptr, count);
 	LAUNCHED(1);
 	d.download(out_host, (size_t) count, s);
 	sb::sync();

@@ -9,9 +9,9 @@ mkdir -p gpurun_out
 LPS=${LPS:-381}     # launches per echelonize step of config 2 (bench prints gpu_launches / steps)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * LPS)) -c $LPS --csv --log-file gpurun_out/launches_config2.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * 1220)) -c 1220 --csv --log-file gpurun_out/launches_config1.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * ${L1:-1218})) -c ${L1:-1218} --csv --log-file gpurun_out/launches_config1.csv \
     python bench.py --workload config1 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench1_under_ncu.log 2>&1
-for k in k_greedy_ooo k_panel_solve_flow k_kahn_async k_rref_panel; do
+for k in k_greedy_ooo k_panel_solve_flow k_kahn_async k_rref_panel_cluster; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_$k \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_$k.log 2>&1
 done

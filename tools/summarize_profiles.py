@@ -3,7 +3,7 @@ import collections, csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1d"
 
 def launches(path, title):
     with open(path) as f:
@@ -54,7 +54,7 @@ md = [f"# profiles/{tag}_ncu_full.md -- `ncu --set full --clock-control none --i
 names = {"k_greedy_ooo": ("greedy_pivot_search", "greedy cycle-free pivot search, out-of-order commits (config 2)"),
          "k_panel_solve_flow": ("panel_solve", "dataflow batched triangular solve (config 2; first batch of the step = the 100-row density estimate)"),
          "k_kahn_async": (None, "asynchronous Kahn levels of the pivot DAG (config 2)"),
-         "k_rref_panel": (None, "dense echelon panel factorisation, 32 columns, one CTA (config 2)"),
+         "k_rref_panel_cluster": (None, "dense echelon panel factorisation, 32 columns, cluster of 8 CTAs (config 2)"),
          "k_umma_gemm_packed": (None, "tcgen05 int8 limb-split modular product, block elimination of config 1 (1000 x <=6813 x 1000, 2 limbs, 128 x 64 tiles)"),
          "k_umma_gemm_packed_8192": ("umma_gemm_8192", "tcgen05 int8 limb-split modular product, 8192 x 8192 x 8192, 2 limbs, 128 x 128 tiles (tools/gemm_bench.py)")}
 for k, (key, title) in names.items():
@@ -72,7 +72,7 @@ for k, (key, title) in names.items():
         traffic[key + "_per_launch"] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
 open(os.path.join(P, f"{tag}_ncu_full.md"), "w").write("".join(md))
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-for f in (f"bench_{tag}.json", f"bench_{tag}_config1.json", f"bench_{tag}_config3.json", f"bench_{tag}_n2.json", "gemm_bench_42013.txt", "gemm_bench_65537.txt", "gemm_bench_2147483629.txt"):
+for f in (f"bench_{tag}.json", f"bench_{tag}_config1.json", f"bench_{tag}_config3.json", f"bench_{tag}_n2.json", f"bench_{tag}_reference.json", "gemm_bench_42013.txt", "gemm_bench_65537.txt", "gemm_bench_2147483629.txt"):
     src = os.path.join(G, f)
     if os.path.exists(src):
         open(os.path.join(P, f), "w").write(open(src).read())
