@@ -367,6 +367,115 @@ static bool rand_rewind_works()
 	return known;
 }
 
+/*
+ * Fast access to the reference's random row choices.  The low-rank finisher draws Sn x w values of glibc's rand() per
+ * block (635 k for config 2) and, with solve-ahead, every value is drawn twice (peeked, then consumed): at ~15 ns per
+ * locked call that was 15-20 ms of a 135 ms step.  glibc's default generator (TYPE_3: r[i] = r[i-31] + r[i-3], output
+ * r[i] >> 1) lives in the table that initstate()/setstate() hand over, so the draws are replayed here on that table
+ * directly and the table is handed back with its position updated.  Checked once against rand() itself; if the libc
+ * behaves differently the code falls back to calling rand().
+ */
+struct FastRand {
+	int32_t *table = nullptr;      /* table[0] = position * 5 + type, table[1..31] = the 31 state words */
+	int rear = 0, front = 0;
+	bool active = false;
+	char saved[256];
+
+	static bool usable()
+	{
+		static int known = -1;
+		if (known >= 0)
+			return known;
+		known = 0;
+		if (getenv("SPASM_B200_NO_FAST_RAND") != NULL || !rand_rewind_works())
+			return false;
+		RandSnapshot s0;
+		if (!rand_snapshot(s0))
+			return false;
+		int want[64];
+		for (int t = 0; t < 64; t++)
+			want[t] = rand();
+		rand_restore(s0);
+		FastRand g;
+		bool same = g.begin();
+		for (int t = 0; same && t < 64; t++)
+			same = (g.next() == want[t]);
+		if (g.active)
+			g.end(false);
+		/* and the hand-over: after a committed run rand() must continue the sequence */
+		if (same) {
+			FastRand h;
+			h.begin();
+			for (int t = 0; t < 10; t++)
+				(void) h.next();
+			h.end(true);
+			for (int t = 10; same && t < 20; t++)
+				same = (rand() == want[t]);
+			rand_restore(s0);
+		}
+		known = same;
+		return known;
+	}
+
+	bool begin()
+	{
+		static char scratch[256];
+		char *old = initstate(1, scratch, sizeof(scratch));       /* park glibc's generator: its table is ours now */
+		if (old == NULL)
+			return false;
+		table = (int32_t *) old;
+		int type = table[0] % 5;
+		if (type != 3) {
+			setstate(old);
+			return false;
+		}
+		rear = table[0] / 5;
+		front = (rear + 3) % 31;
+		memcpy(saved, old, 128);
+		active = true;
+		return true;
+	}
+
+	inline int next()
+	{
+		uint32_t *st = (uint32_t *) (table + 1);
+		uint32_t val = (st[front] += st[rear]);
+		if (++front >= 31) {
+			front = 0;
+			++rear;
+		} else if (++rear >= 31) {
+			rear = 0;
+		}
+		return (int) (val >> 1);
+	}
+
+	void end(bool commit)
+	{
+		if (!active)
+			return;
+		if (commit)
+			table[0] = rear * 5 + 3;
+		else
+			memcpy(table, saved, 128);
+		setstate((char *) table);
+		active = false;
+	}
+};
+
+/* `count` draws of rand(), thrown away (the blocks solved ahead consume their draws when they are processed) */
+static void rand_skip(i64 count)
+{
+	FastRand g;
+	if (FastRand::usable() && g.begin()) {
+		for (i64 t = 0; t < count; t++)
+			(void) g.next();
+		g.end(true);
+	} else {
+		for (i64 t = 0; t < count; t++)
+			(void) rand();
+	}
+}
+
 struct AheadBlock { int Sn, n, w; };          /* predicted shape of a low-rank block */
 
 /* Row choices and coefficients of several predicted low-rank blocks, as the reference will draw them; rand() is left
@@ -375,8 +484,6 @@ static size_t peek_combinations(Engine &E, const int *p, const std::vector<Ahead
                                 std::vector<int> &offset)
 {
 	cudaStream_t s = ctx().stream;
-	RandSnapshot snap;
-	rand_snapshot(snap);
 	int w = plan[0].w;
 	size_t total = 0;
 	offset.clear();
@@ -388,13 +495,33 @@ static size_t peek_combinations(Engine &E, const int *p, const std::vector<Ahead
 	d_coef.alloc(total * w);
 	size_t at = 0;
 	for (const AheadBlock &b : plan) {
-		for (int k = 0; k < b.Sn; k++)
-			for (int t = 0; t < w; t++)
-				rows[(at + k) * w + t] = p[rand() % b.n];
 		prng_combo_coefficients(E.prime, b.Sn, w, d_coef.ptr + at * w);     /* streams are seeded per row OF ITS BLOCK */
 		at += b.Sn;
 	}
-	rand_restore(snap);
+	FastRand g;
+	if (FastRand::usable() && g.begin()) {
+		at = 0;
+		for (const AheadBlock &b : plan) {
+			/* x % n without a division (Lemire): n is the same for the whole block */
+			const uint64_t M = UINT64_MAX / (uint32_t) b.n + 1;
+			for (size_t e = at * w; e < (at + b.Sn) * w; e++) {
+				const uint64_t low = M * (uint32_t) g.next();
+				rows[e] = p[(uint32_t) (((unsigned __int128) low * (uint32_t) b.n) >> 64)];
+			}
+			at += b.Sn;
+		}
+		g.end(false);                    /* peek: the table goes back as it was */
+	} else {
+		RandSnapshot snap;
+		rand_snapshot(snap);
+		at = 0;
+		for (const AheadBlock &b : plan) {
+			for (size_t e = at * w; e < (at + b.Sn) * w; e++)
+				rows[e] = p[rand() % b.n];
+			at += b.Sn;
+		}
+		rand_restore(snap);
+	}
 	d_rows.upload(rows.data(), rows.size(), s);
 	sync();                              /* `rows` is a local */
 	stats().pub.h2d_bytes += (i64) rows.size() * 4;
@@ -476,6 +603,16 @@ static double estimate_density_speculative(Engine &E, const DevCsr &A, const int
 	if (off || n == 0 || Sm <= 0 || E.dense_ready)
 		return estimate_density(E, A, p, n, R);
 	cudaStream_t s = ctx().stream;
+	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
+	double t_prev = spasm_wtime();
+	auto lap = [&](const char *what) {
+		if (trace) {
+			sync();
+			double now = spasm_wtime();
+			fprintf(stderr, "[trace]   density+batch/%-14s %8.3f ms\n", what, 1e3 * (now - t_prev));
+			t_prev = now;
+		}
+	};
 	/* 1. the estimate's own draws */
 	std::vector<int> rows(R);
 	for (int t = 0; t < R; t++)
@@ -510,6 +647,7 @@ static double estimate_density_speculative(Engine &E, const DevCsr &A, const int
 		i64 nnz0 = panel_count_nonzero(E.panel, E.Uqinv.ptr);
 		return ((double) nnz0) / Sm / R;
 	}
+	lap("draws");
 	/* 3. one pass for both */
 	if (!E.G_ready)
 		E.rebuild_schedule();
@@ -522,10 +660,14 @@ static double estimate_density_speculative(Engine &E, const DevCsr &A, const int
 		panel_scatter_combos(A, d_rows2.ptr, d_coef.ptr, N, spec.w, E.panel, E.F, R_off);
 	else
 		panel_scatter_rows(A, d_rows2.ptr, N, E.panel, E.F, false, R_off);
+	lap("scatter");
 	panel_solve(E.G, E.panel.X, E.panel.ld, R_off + N, E.F);
 	stats().pub.ms_solve += t.stop_ms();
+	lap("solve");
 	E.account_bytes(R_off + N);
+	lap("byte accounting");
 	i64 nnz = panel_count_nonzero(E.panel, E.Uqinv.ptr, R);
+	lap("count");
 	/* 4. the finisher's batch as a dense block over the columns that are not pivotal now */
 	E.begin_dense();
 	spec.froze_columns = true;
@@ -535,6 +677,7 @@ static double estimate_density_speculative(Engine &E, const DevCsr &A, const int
 	spec.n = n;
 	spec.valid = true;
 	sync();
+	lap("gather");
 	return ((double) nnz) / Sm / R;
 }
 
@@ -570,8 +713,7 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 		i32 *block = nullptr;
 		if (next_ahead < plan.size() && plan[next_ahead].Sn == Sn && plan[next_ahead].n == n && plan[next_ahead].w == w) {
 			/* the prediction holds: consume this block's rand() draws like the reference, use the solved rows */
-			for (i64 t = 0; t < (i64) Sn * w; t++)
-				(void) rand();
+			rand_skip((i64) Sn * w);
 			block = ahead.ptr + (size_t) ahead_offset[next_ahead] * ahead_ld;
 			ldB = ahead_ld;
 			next_ahead++;
@@ -582,8 +724,7 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 				plan = plan_lowrank(n, rank_ub, w, opts);      /* predict: every block has full rank and keeps the weight */
 			if (plan.size() > 1) {
 				randomized_blocks_ahead(E, A, p, plan, ahead, ahead_ld, ahead_offset);
-				for (i64 t = 0; t < (i64) Sn * w; t++)
-					(void) rand();
+				rand_skip((i64) Sn * w);
 				block = ahead.ptr;
 				ldB = ahead_ld;
 				next_ahead = 1;
