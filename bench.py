@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                 for nm, bit in flags.items():
                     if mask & bit:
                         self.reasons.add(nm)
-                self.stop_flag.wait(0.05)
+                self.stop_flag.wait(0.2)       # NVML queries take driver locks: keep them rare
             return
         except Exception:
             pass

@@ -6,6 +6,7 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_o
 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_r1d.err | tail -1 > gpurun_out/bench_r1d.json
 python bench.py --workload config1 --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_r1d_config1.json
 python bench.py --workload config3 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_r1d_config3.json
+python bench.py --workload config5 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_r1d_config5.json
 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_r1d_reference.json
 LPS=$(python -c "import json; d=json.load(open('gpurun_out/bench_r1d.json')); print(d['gpu_launches']//d['steps'])")
 L1=$(python -c "import json; d=json.load(open('gpurun_out/bench_r1d_config1.json')); print(d['gpu_launches']//d['steps'])")
