@@ -8,7 +8,7 @@
 #include "stats.cuh"
 
 namespace sb {
-int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round);
+int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round, bool allow_lazy);
 double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R);
 void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S);
 
@@ -126,7 +126,7 @@ int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, 
 	dA.upload(A);
 	stats().pair_row.clear();
 	stats().pair_col.clear();
-	int npiv = extract_structural(E, dA, p_in, p, opts->enable_greedy_pivot_search, 0);
+	int npiv = extract_structural(E, dA, p_in, p, opts->enable_greedy_pivot_search, 0, false);      /* this entry point returns U and p at once: eager levels */
 	/* append the new rows to the caller's U */
 	i64 extra = E.U.nnz - unz0;
 	if (spasm_nnz(U) + extra > U->nzmax)

@@ -70,7 +70,7 @@ __global__ void k_add_offset(i64 *p, int count, i64 off)
  * p (host, size A.n) receives the row permutation: pivotal rows first (in the order they get in U),
  * then the other rows by increasing index.
  */
-int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round)
+int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round, bool allow_lazy)
 {
 	GpuTimer timer;
 	timer.start();
@@ -111,11 +111,29 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 		int got = compact_flagged(rows_all.ptr, flags.ptr, m, rows_tmp.ptr);
 		if (got != npiv)
 			errx(1, "[spasm-b200] internal: pivot count mismatch (%d vs %d)", got, npiv);
+		lap("select rows");
+		if (allow_lazy && E.U.n == 0) {
+			/* First round of an echelonization: the rows go to U in column order and only what the dataflow solve
+			 * needs is scheduled.  The levels of the pivot DAG (a full traversal: 14 ms on config 2) come out of
+			 * the first solve pass, and assemble() puts the rows in level order at the end. */
+			append_pivotal_rows(A, rows_tmp.ptr, npiv, d_pinv.ptr, E.U, E.Uqinv);
+			lap("U (column order)");
+			E.G = DepGraph();
+			depgraph_forward(E.U, E.G);
+			lap("depgraph_forward");
+			depgraph_schedule(E.G, true);
+			lap("depgraph_schedule (lazy)");
+			E.G_ready = true;
+			E.lazy_rows = E.G.levels_known ? 0 : npiv;
+			st.pub.dag_depth = E.G.nlevels;
+			h_rows.resize(npiv);
+			rows_tmp.download(h_rows.data(), (size_t) npiv, s);
+			sync();
+		} else {
 		DevCsr Unew;
 		Unew.m = m;
 		Unew.prime = A.prime;
 		DevBuf<int> scratch_qinv((size_t) m);
-		lap("select rows");
 		append_pivotal_rows(A, rows_tmp.ptr, npiv, d_pinv.ptr, Unew, scratch_qinv);
 		lap("U (column order)");
 		DepGraph Gnew;
@@ -142,6 +160,7 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 			st.pub.dag_depth = E.G.nlevels;
 		} else {
 			E.G_ready = false;
+		}
 		}
 	}
 	sync();
@@ -842,10 +861,55 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	int rank = E.rank();
 	struct spasm_csr *U = spasm_csr_alloc(std::max(rank, n_rows_alloc), E.m, std::max<i64>(total, 1), E.prime, true);
 	int *qinv = (int *) spasm_malloc((i64) std::max(E.m, 1) * sizeof(int));
-	E.U.p.download(U->p, (size_t) E.U.n + 1, s);
-	E.U.j.download(U->j, (size_t) E.U.nnz, s);
-	E.U.x.download(U->x, (size_t) E.U.nnz, s);
 	E.Uqinv.download(qinv, (size_t) E.m, s);
+	if (E.lazy_rows > 0) {
+		/* The first lazy_rows rows of U are in column order (lazy schedule, extract_structural).  Put them in
+		 * (level, column) order like the eager path does: the levels came out of the first solve pass; if no solve
+		 * ever ran, or if later rounds invalidated the schedule, they are computed now. */
+		if (!E.G_ready || !E.G.levels_known) {
+			E.G = DepGraph();
+			depgraph_forward(E.U, E.G);
+			depgraph_schedule(E.G);
+			E.G_ready = true;
+			stats().pub.dag_depth = E.G.nlevels;
+		}
+		const int L = E.lazy_rows;
+		std::vector<int> order((size_t) E.m);
+		std::vector<i64> hp((size_t) E.U.n + 1);
+		std::vector<int> hj((size_t) std::max<i64>(E.U.nnz, 1));
+		std::vector<i32> hx((size_t) std::max<i64>(E.U.nnz, 1));
+		E.G.order.download(order.data(), (size_t) E.m, s);
+		E.U.p.download(hp.data(), hp.size(), s);
+		E.U.j.download(hj.data(), (size_t) E.U.nnz, s);
+		E.U.x.download(hx.data(), (size_t) E.U.nnz, s);
+		sync();
+		std::vector<int> perm;            /* perm[new position] = row of E.U */
+		perm.reserve(E.U.n);
+		for (int t = 0; t < E.m; t++) {
+			int r = qinv[order[t]];
+			if (r >= 0 && r < L)
+				perm.push_back(r);
+		}
+		if ((int) perm.size() != L)
+			errx(1, "[spasm-b200] internal: level order covers %zu of %d structural rows", perm.size(), L);
+		for (int r = L; r < E.U.n; r++)
+			perm.push_back(r);
+		i64 at = 0;
+		for (int t = 0; t < E.U.n; t++) {
+			const int r = perm[t];
+			const i64 len = hp[r + 1] - hp[r];
+			U->p[t] = at;
+			memcpy(U->j + at, hj.data() + hp[r], (size_t) len * sizeof(int));
+			memcpy(U->x + at, hx.data() + hp[r], (size_t) len * sizeof(i32));
+			qinv[hj[hp[r]]] = t;              /* the pivot is the first entry of the row */
+			at += len;
+		}
+		U->p[E.U.n] = at;
+	} else {
+		E.U.p.download(U->p, (size_t) E.U.n + 1, s);
+		E.U.j.download(U->j, (size_t) E.U.nnz, s);
+		E.U.x.download(U->x, (size_t) E.U.nnz, s);
+	}
 	sync();
 	lap("structural rows");
 	i64 off = E.U.nnz;
@@ -928,7 +992,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			break;
 		}
 		LOG("[echelonize] round %d\n", round);
-		npiv = extract_structural(E, *cur, p_in.empty() ? NULL : p_in.data(), p.data(), opts->enable_greedy_pivot_search, round);
+		npiv = extract_structural(E, *cur, p_in.empty() ? NULL : p_in.data(), p.data(), opts->enable_greedy_pivot_search, round, true);
 		lap("extract_structural");
 		st.pub.nrounds = round + 1;
 		st.pair_start.push_back((int) st.pair_row.size());

@@ -17,6 +17,7 @@ void Engine::init(int m_, i64 prime_)
 	Uqinv.fill_byte(0xff, ctx().stream);
 	G = DepGraph();
 	G_ready = false;
+	lazy_rows = 0;
 	dense_ready = false;
 	blocks.clear();
 	dense_rank = 0;

@@ -33,6 +33,7 @@ struct Engine {
 	DevBuf<int> Uqinv;               /* size m; row of U (structural index) or -1 */
 	DepGraph G;                      /* forward dependency graph of U, scheduled */
 	bool G_ready = false;
+	int lazy_rows = 0;               /* the first lazy_rows rows of U are in column order: assemble() puts them in level order */
 	/* dense part, over the columns that are non-pivotal after the structural rounds */
 	bool dense_ready = false;
 	int Sm0 = 0;

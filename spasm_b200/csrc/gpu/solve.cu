@@ -307,7 +307,55 @@ __global__ void k_flow_prepare(int n, const i64 *__restrict__ ptr, const int *__
 		seeds[atomicAdd(nseeds, 1)] = c;
 }
 
-void depgraph_schedule(DepGraph &G)
+void depgraph_finish_levels(DepGraph &G)
+{
+	cudaStream_t s = ctx().stream;
+	const int n = G.nnodes;
+	/* deterministic order inside each level: sort by (level, node); level boundaries by binary search on the keys */
+	DevBuf<unsigned long long> keys((size_t) n), keys2((size_t) n);
+	k_make_keys<<<cdiv(n, 256), 256, 0, s>>>(n, G.order, G.level, keys.ptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
+	k_keys_to_order<<<cdiv(n, 256), 256, 0, s>>>(n, keys2.ptr, G.order);
+	unsigned long long last_key = 0;
+	CUDA_CHECK(cudaMemcpyAsync(&last_key, keys2.ptr + (n - 1), sizeof(last_key), cudaMemcpyDeviceToHost, s));
+	sync();
+	G.nlevels = (int) (last_key >> 32) + 1;
+	k_level_bounds<<<cdiv(G.nlevels + 1, 256), 256, 0, s>>>(n, keys2.ptr, G.nlevels, G.level_ptr.ptr);
+	LAUNCHED(4);
+	KERNEL_CHECK();
+	G.level_ptr_h.resize((size_t) G.nlevels + 1);
+	CUDA_CHECK(cudaMemcpyAsync(G.level_ptr_h.data(), G.level_ptr.ptr, ((size_t) G.nlevels + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+	sync();
+	G.levels_known = true;
+}
+
+/* lazy schedule: pending0[c] = dependencies of c that have dependencies themselves; seeds = nodes with dependencies all
+ * of whose dependencies are sources; *nsched = nodes with dependencies */
+__global__ void k_flow_prepare_lazy(int n, const i64 *__restrict__ ptr, const int *__restrict__ src, int *pending0, int *seeds,
+                                    int *nseeds, int *nsched)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n)
+		return;
+	const i64 b = ptr[c], e = ptr[c + 1];
+	int cnt = 0;
+	for (i64 k = b; k < e; k++) {
+		const int sc = src[k];
+		cnt += ptr[sc + 1] > ptr[sc];
+	}
+	pending0[c] = cnt;
+	if (e > b) {
+		atomicAdd(nsched, 1);
+		if (cnt == 0)
+			seeds[atomicAdd(nseeds, 1)] = c;
+	}
+}
+
+void depgraph_schedule(DepGraph &G, bool lazy)
 {
 	cudaStream_t s = ctx().stream;
 	static const bool trace = getenv("SPASM_B200_TRACE") != NULL;
@@ -341,6 +389,28 @@ void depgraph_schedule(DepGraph &G)
 	exclusive_scan_i64(rcnt.ptr, rptr.ptr, (size_t) n + 1);
 	CUDA_CHECK(cudaMemcpyAsync(rcnt.ptr, rptr.ptr, ((size_t) n + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
 	k_rev_fill<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, (unsigned long long *) rcnt.ptr, rdst);
+	static const bool force_eager = getenv("SPASM_B200_EAGER_LEVELS") != NULL || getenv("SPASM_B200_SOLVE_LEVELS") != NULL;
+	if (lazy && !force_eager) {
+		G.level.zero(s);                      /* sources stay at level 0; the solve fills the rest */
+		G.pending0.alloc((size_t) n);
+		G.seeds.alloc((size_t) n);
+		k_flow_prepare_lazy<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr, G.src, G.pending0.ptr, G.seeds.ptr, counters.ptr, counters.ptr + 1);
+		LAUNCHED(3);
+		KERNEL_CHECK();
+		int hc[2];
+		CUDA_CHECK(cudaMemcpyAsync(hc, counters.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+		sync();
+		G.nseeds = hc[0];
+		G.nscheduled = hc[1];
+		G.nlevels = G.nscheduled > 0 ? 2 : 1;         /* placeholder until the first solve */
+		G.level_ptr_h.assign({0, n - G.nscheduled, n});
+		G.scheduled_deps = G.ndeps;
+		G.levels_known = false;
+		lap("lazy schedule");
+		if (G.nscheduled == 0)
+			depgraph_finish_levels(G);        /* no dependency at all: every node is at level 0 */
+		return;
+	}
 	DevBuf<unsigned long long> state((size_t) n);
 	k_kahn_seed<<<cdiv(n, 256), 256, 0, s>>>(n, indeg, G.order, state.ptr, counters.ptr);
 	LAUNCHED(3);
@@ -389,25 +459,7 @@ void depgraph_schedule(DepGraph &G)
 		        "error flag %d): %s", h[3], n, seen, h[2], seen == n ? "internal error of the device scheduler" : "invalid U / qinv");
 	}
 
-	/* deterministic order inside each level: sort by (level, node); level boundaries by binary search on the keys */
-	DevBuf<unsigned long long> keys((size_t) n), keys2((size_t) n);
-	k_make_keys<<<cdiv(n, 256), 256, 0, s>>>(n, G.order, G.level, keys.ptr);
-	static DevBuf<char> tmp;
-	size_t bytes = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
-	tmp.ensure(bytes + 16);
-	cub::DeviceRadixSort::SortKeys(tmp.ptr, bytes, keys.ptr, keys2.ptr, n, 0, 64, s);
-	k_keys_to_order<<<cdiv(n, 256), 256, 0, s>>>(n, keys2.ptr, G.order);
-	unsigned long long last_key = 0;
-	CUDA_CHECK(cudaMemcpyAsync(&last_key, keys2.ptr + (n - 1), sizeof(last_key), cudaMemcpyDeviceToHost, s));
-	sync();
-	G.nlevels = (int) (last_key >> 32) + 1;
-	k_level_bounds<<<cdiv(G.nlevels + 1, 256), 256, 0, s>>>(n, keys2.ptr, G.nlevels, G.level_ptr.ptr);
-	LAUNCHED(4);
-	KERNEL_CHECK();
-	G.level_ptr_h.resize((size_t) G.nlevels + 1);
-	CUDA_CHECK(cudaMemcpyAsync(G.level_ptr_h.data(), G.level_ptr.ptr, ((size_t) G.nlevels + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-	sync();
+	depgraph_finish_levels(G);
 	/* dataflow schedule of the solve */
 	G.pending0.alloc((size_t) n);
 	G.seeds.alloc((size_t) n);
@@ -506,7 +558,7 @@ __global__ void __launch_bounds__(1024)
 k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                    const i64 *__restrict__ rptr, const int *__restrict__ rdst, const int *__restrict__ level,
                    int *pending, int *queue, int nseeds, int nscheduled, int *tail, int *ticket, int *done, int *error,
-                   int4 *X, int ld4, int R4, Zp F)
+                   int4 *X, int ld4, int R4, Zp F, int *level_out)
 {
 	/* The critical path of a pass is a chain of the DAG walked by one CTA.  To keep a hop short, the metadata of the
 	 * columns that depend on the current one (their dependency lists) is prefetched into shared memory while the
@@ -639,6 +691,16 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
 				Xc[r] = b;
 			}
+		}
+		/* lazy schedule: the level of the column, 1 + max over its dependencies (all final: they released this
+		 * column), is a by-product of the pass; published by the fence below with the column itself */
+		if (level_out && tid == blockDim.x - 1) {
+			const int cnt = cur.cnt;
+			const i64 e0 = cur.e0;
+			int lv = 0;
+			for (int e = 0; e < cnt; e++)
+				lv = max(lv, __ldcg(&level_out[(e < FLOW_MAXE) ? cur.src[e] : src[e0 + e]]));
+			level_out[c] = lv + 1;
 		}
 		__threadfence();
 		if (tid == 0)
@@ -773,6 +835,8 @@ void panel_solve_masked(const DepGraph &G, i32 *X, int ld, int R, unsigned *mask
 {
 	if (G.nlevels <= 1 || R <= 0 || G.nscheduled <= 0)
 		return;
+	if (!G.levels_known)
+		errx(1, "[spasm-b200] internal: the masked solve needs an eagerly scheduled graph");
 	if (ld % 4 != 0)
 		errx(1, "[spasm-b200] internal: panel leading dimension must be a multiple of 4");
 	int R4 = (R + 3) / 4, ld4 = ld / 4;
@@ -819,7 +883,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 	int R4 = (R + 3) / 4, ld4 = ld / 4;
 	cudaStream_t s = ctx().stream;
 	static const bool use_levels = getenv("SPASM_B200_SOLVE_LEVELS") != NULL;
-	if (!use_levels && G.nscheduled > 0) {
+	if ((!use_levels || !G.levels_known) && G.nscheduled > 0) {
 		int n = G.nnodes;
 		DevBuf<int> pending((size_t) n), queue((size_t) n + 1), counters(4);
 		CUDA_CHECK(cudaMemcpyAsync(pending.ptr, G.pending0.ptr, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -836,15 +900,25 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		tk.start();
 		k_panel_solve_flow<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, G.level.ptr, pending.ptr, queue.ptr,
 		                                         G.nseeds, G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3,
-		                                         (int4 *) X, ld4, R4, F);
+		                                         (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr);
 		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_panel_solve += tk.stop_ms();
 		int h[4];
 		CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
 		sync();
-		if (h[3] != 0 || h[2] != G.nscheduled)
+		if (h[3] != 0 || h[2] != G.nscheduled) {
+			if (!G.levels_known)      /* lazy schedule: this pass is also the cycle check */
+				errx(1, "[spasm-b200] the pivots do not form a triangular system (%d of %d dependent columns solved): invalid U / qinv",
+				     h[2], G.nscheduled);
 			errx(1, "[spasm-b200] internal: dataflow solve did not complete (%d of %d columns)", h[2], G.nscheduled);
+		}
+		if (!G.levels_known) {
+			/* the graph is logically const for a solve; completing its lazily built schedule is the one exception */
+			DepGraph &Gm = const_cast<DepGraph &>(G);
+			depgraph_finish_levels(Gm);
+			stats().pub.dag_depth = Gm.nlevels;
+		}
 		Stats &st = stats();
 		st.pub.solve_batches += 1;
 		st.pub.solve_rows += R;
