@@ -550,6 +550,7 @@ struct FlowMeta {
 	int node;
 	int cnt;             /* number of dependencies (may exceed FLOW_MAXE: the rest is read from global memory) */
 	i64 e0;
+	i64 rb, re;          /* its dependents: rdst[rb:re] */
 	int src[FLOW_MAXE];
 	i32 val[FLOW_MAXE];
 };
@@ -579,6 +580,8 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 				cur.node = dep[next_slot].node;
 				cur.cnt = dep[next_slot].cnt;
 				cur.e0 = dep[next_slot].e0;
+				cur.rb = dep[next_slot].rb;
+				cur.re = dep[next_slot].re;
 			}
 		} else {
 			if (tid == 0) {
@@ -617,35 +620,46 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 				cur.node = c0;
 				cur.cnt = cnt;
 				cur.e0 = e0;
+				cur.rb = rptr[c0];
+				cur.re = rptr[c0 + 1];
 			}
 		}
 		__syncthreads();
 		const int c = cur.node;
-		const i64 rb = rptr[c], re = rptr[c + 1];
-		/* ---- 2. prefetch the metadata of the dependents (overlaps with the loads of the column below) */
-		if (tid < FLOW_MAXD * FLOW_MAXE) {
-			const int di = tid / FLOW_MAXE, ei = tid % FLOW_MAXE;
-			if (rb + di < re) {
-				const int d = rdst[rb + di];
-				const i64 de0 = ptr[d];
-				const int dcnt = (int) (ptr[d + 1] - de0);
-				if (ei < dcnt) {
-					dep[di].src[ei] = src[de0 + ei];
-					dep[di].val[ei] = val[de0 + ei];
-				}
-				if (ei == 0) {
-					dep[di].node = d;
-					dep[di].cnt = dcnt;
-					dep[di].e0 = de0;
+		const i64 rb = cur.rb, re = cur.re;
+		/* ---- 2. the LAST WARP prefetches the metadata of the dependents (their dependency lists and their own lists
+		 * of dependents): a chain of four dependent loads that used to be issued by threads that also compute the
+		 * column, which put it in front of the column's own loads on the critical path of a hop */
+		/* (when the batch is wider than the CTA every thread computes and the first 64 threads prefetch first) */
+		const bool dedicated = R4 <= (int) blockDim.x - 32;
+		const int T3 = dedicated ? blockDim.x - 32 : blockDim.x;          /* threads that compute the column */
+		if (dedicated ? tid >= T3 : tid < FLOW_MAXD * FLOW_MAXE) {
+			for (int item = dedicated ? tid - T3 : tid; item < FLOW_MAXD * FLOW_MAXE; item += dedicated ? 32 : FLOW_MAXD * FLOW_MAXE) {
+				const int di = item / FLOW_MAXE, ei = item % FLOW_MAXE;
+				if (rb + di < re) {
+					const int d = rdst[rb + di];
+					const i64 de0 = ptr[d];
+					const int dcnt = (int) (ptr[d + 1] - de0);
+					if (ei < dcnt) {
+						dep[di].src[ei] = src[de0 + ei];
+						dep[di].val[ei] = val[de0 + ei];
+					}
+					if (ei == 0) {
+						dep[di].node = d;
+						dep[di].cnt = dcnt;
+						dep[di].e0 = de0;
+						dep[di].rb = rptr[d];
+						dep[di].re = rptr[d + 1];
+					}
 				}
 			}
 		}
 		/* ---- 3. the column, for all right-hand sides; dependencies are read around L1 (written by other SMs) */
-		{
+		if (tid < T3) {
 			const int cnt = cur.cnt, cached = min(cnt, FLOW_MAXE);
 			const i64 e0 = cur.e0;
 			int4 *Xc = X + (size_t) c * ld4;
-			for (int r = tid; r < R4; r += blockDim.x) {
+			for (int r = tid; r < R4; r += T3) {
 				int4 b = Xc[r];
 				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
 				int pendingred = 0;
@@ -892,7 +906,8 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		int h_init[4] = {G.nseeds, 0, 0, 0};      /* tail, ticket, done, error */
 		CUDA_CHECK(cudaMemcpyAsync(counters.ptr, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
 		/* one pass over the right-hand sides per column when possible: the column is the unit of the critical path */
-		int threads = getenv("SPASM_B200_FLOW_THREADS") ? atoi(getenv("SPASM_B200_FLOW_THREADS")) : (R4 > 512 ? 1024 : R4 > 256 ? 512 : 256);
+		int threads = getenv("SPASM_B200_FLOW_THREADS") ? atoi(getenv("SPASM_B200_FLOW_THREADS")) : (R4 > 480 ? 1024 : R4 > 224 ? 512 : 256);      /* one warp of the CTA is the prefetcher when the batch fits */
+		threads = std::max(64, std::min(1024, threads & ~31));
 		int occ = 0;
 		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, threads, 0));
 		int blocks = std::max(1, std::min(occ, 8)) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
