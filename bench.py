@@ -22,7 +22,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -58,60 +57,54 @@ def make_workload(name: str, scale: float):
     return t, opts
 
 
-class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe), through NVML (nvidia-smi as a fallback)."""
+class ClockSampler:
+    """SM clock / throttle reasons inside the timed region (B200_PROFILING.md recipe), sampled BETWEEN the timed steps:
+    right after a step's last kernel, before the next one starts.  Every step is timed on its own (CUDA events inside
+    the library, perf_counter around the C call for e2e), so a sample never sits inside a measured interval.  Sampling
+    concurrently was tried three ways and perturbed the measurement each time: forking nvidia-smi from this process
+    (GBs of mappings: the page-table copy stalled the timed thread ~20 ms), NVML from a thread, and NVML from a helper
+    process (the queries take driver locks that CUDA calls wait for: +35 to +150 ms on the step they hit)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.stop_flag = threading.Event()
-        self.max_mhz = None
-
-    def run(self):
-        # NVML in-process when available: forking nvidia-smi from a process that holds a CUDA context and GBs of mapped
-        # memory stalls the timed thread for tens of milliseconds (page-table copy under the mm lock)
+        self.index, self.samples, self.reasons, self.max_mhz, self.h = index, [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of indices
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
             ids = [int(x) for x in vis.split(",") if x.strip().isdigit()] if vis else []
-            h = pynvml.nvmlDeviceGetHandleByIndex(ids[self.index] if self.index < len(ids) else self.index)
-            flags = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            while not self.stop_flag.is_set():
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                mask = get_reasons(h)
-                for nm, bit in flags.items():
-                    if mask & bit:
-                        self.reasons.add(nm)
-                self.stop_flag.wait(0.2)       # NVML queries take driver locks: keep them rare
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if index < len(ids) else index)
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def sample(self):
+        if os.environ.get("SPASM_B200_BENCH_NO_CLOCKS"):
             return
+        try:
+            if self.h is not None:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = self.get(self.h)
+                self.reasons.update(n for n, b in zip(self.NAMES, self.bits) if mask & b)
+                return
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            self.samples.append(float(out[0]))
+            self.max_mhz = float(out[1])
+            self.reasons.update(n for n, v in zip(self.NAMES, out[2:6]) if v.strip().lower() == "active")
         except Exception:
             pass
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:6]):
-                    if v.strip().lower() == "active":
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
 
     def summary(self) -> dict:
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "when": "between timed steps"}
 
 
 def run_reference(args) -> None:
@@ -198,6 +191,7 @@ def main() -> None:
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local_rank)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("SPASM_B200_DEVICE", str(local_rank))
 
@@ -233,8 +227,6 @@ def main() -> None:
     for _ in range(max(args.warmup, 3)):
         oracle.reset_rand()
         L.spasm_b200_echelonize_resident(handle, C.byref(o), C.byref(ms))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     step_ms, agg = [], None
     wall0 = time.perf_counter()
@@ -244,6 +236,7 @@ def main() -> None:
         L.spasm_b200_reset_stats()
         rk = L.spasm_b200_echelonize_resident(handle, C.byref(o), C.byref(ms))
         step_ms.append(ms.value)
+        sampler.sample()                     # right after the step's last kernel; outside every measured interval
         s = spasm_b200.Stats()
         L.spasm_b200_get_stats(C.byref(s))
         if agg is None:
@@ -254,8 +247,6 @@ def main() -> None:
             agg[k] += float(getattr(s, k))
     barrier()
     wall = time.perf_counter() - wall0
-    sampler.stop_flag.set()
-    sampler.join()
     total_ms = sum(step_ms)
 
     # ---- end-to-end steps through the reference-facing C ABI (host buffers in, host echelon form out)

@@ -51,6 +51,15 @@ Stats &stats();
 size_t bulk_download_threshold();      /* 2 MB; SPASM_B200_BULK_MB overrides (read at every call: the tests toggle it) */
 void download_bulk(void *host, const void *dev, size_t bytes);
 
+/* -------------------------------------------------------------------- device memory
+ * cudaMallocAsync from the device pool, plus a small cache of the LARGE blocks (>= 32 MB: panels, search queues, stacked
+ * dense blocks) owned by the library: returned to the pool at every call they were split by the smaller allocations
+ * that followed, and every few echelonizations the pool had to map a fresh 1.4 GB block for the next panel -- a 600 ms
+ * stall in the middle of a 110 ms step.  Everything runs on one stream, so a cached block can be handed out again as
+ * soon as it is released. */
+void *device_alloc(size_t bytes);
+void device_free(void *ptr, size_t bytes);
+
 /* -------------------------------------------------------------------- device buffers */
 template <typename T> struct DevBuf {
 	T *ptr = nullptr;
@@ -75,13 +84,13 @@ template <typename T> struct DevBuf {
 		release();
 		count = n;
 		if (n > 0)
-			CUDA_CHECK(cudaMallocAsync((void **) &ptr, n * sizeof(T), ctx().stream));
+			ptr = (T *) device_alloc(n * sizeof(T));
 	}
 	/* grow (contents are NOT preserved) */
 	void ensure(size_t n) { if (n > count) alloc(n); }
 	void release() {
 		if (ptr)
-			cudaFreeAsync(ptr, ctx().stream);
+			device_free(ptr, count * sizeof(T));
 		ptr = nullptr;
 		count = 0;
 	}

@@ -71,6 +71,73 @@ static void parallel_memcpy(char *dst, const char *src, size_t bytes, int nthrea
 		th.join();
 }
 
+/* ---- large-block cache (common.cuh) */
+static const size_t BIG_BLOCK = (size_t) 32 << 20;
+struct CachedBlock { void *ptr; size_t bytes; };
+static std::vector<CachedBlock> g_cache;       /* free blocks */
+static std::vector<CachedBlock> g_live_big;    /* blocks handed out from the cache (they may be larger than what was asked for) */
+static size_t g_cache_bytes = 0;
+static size_t cache_limit()
+{
+	static size_t limit = 0;
+	if (!limit) {
+		const char *e = getenv("SPASM_B200_CACHE_GB");
+		limit = (size_t) ((e ? atof(e) : 48.0) * 1e9);
+	}
+	return limit;
+}
+
+void *device_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (bytes >= BIG_BLOCK) {
+		/* best fit among the cached blocks that are not wastefully large */
+		int best = -1;
+		for (int k = 0; k < (int) g_cache.size(); k++)
+			if (g_cache[k].bytes >= bytes && g_cache[k].bytes <= 2 * bytes && (best < 0 || g_cache[k].bytes < g_cache[best].bytes))
+				best = k;
+		if (best >= 0) {
+			p = g_cache[best].ptr;
+			g_cache_bytes -= g_cache[best].bytes;
+			g_live_big.push_back({p, g_cache[best].bytes});
+			g_cache.erase(g_cache.begin() + best);
+			return p;
+		}
+	}
+	cudaError_t e = cudaMallocAsync(&p, bytes, ctx().stream);
+	if (e != cudaSuccess && !g_cache.empty()) {
+		/* out of memory with blocks parked in the cache: give them back and retry */
+		(void) cudaGetLastError();
+		for (CachedBlock &b : g_cache)
+			cudaFreeAsync(b.ptr, ctx().stream);
+		g_cache.clear();
+		g_cache_bytes = 0;
+		CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+		e = cudaMallocAsync(&p, bytes, ctx().stream);
+	}
+	CUDA_CHECK(e);
+	return p;
+}
+
+void device_free(void *ptr, size_t bytes)
+{
+	if (bytes >= BIG_BLOCK) {
+		size_t true_bytes = bytes;
+		for (size_t k = 0; k < g_live_big.size(); k++)
+			if (g_live_big[k].ptr == ptr) {
+				true_bytes = g_live_big[k].bytes;
+				g_live_big.erase(g_live_big.begin() + k);
+				break;
+			}
+		if (g_cache_bytes + true_bytes <= cache_limit()) {
+			g_cache.push_back({ptr, true_bytes});
+			g_cache_bytes += true_bytes;
+			return;
+		}
+	}
+	cudaFreeAsync(ptr, ctx().stream);
+}
+
 size_t bulk_download_threshold()
 {
 	const char *e = getenv("SPASM_B200_BULK_MB");
