@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -197,3 +198,15 @@ def test_tensor_core_path_is_really_tcgen05():
     assert "LDTM" in sass and "UTCBAR" in sass
     assert "UBLKCP" in sass, "no bulk-copy (TMA engine) operand pipeline in the SASS"
     assert " IMMA." not in sass and " HMMA." not in sass
+
+
+def test_bench_cli_and_clock_sampler_work_without_a_gpu():
+    """bench.py must at least parse, print its usage, and its clock sampler must degrade to "no samples" (not crash)
+    on a machine without NVML / nvidia-smi: the driver imports and launches it unconditionally."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "--impl" in out.stdout and "--gpus" in out.stdout
+    code = ("import sys; sys.path.insert(0, %r); import bench; s = bench.ClockSampler(0); s.sample(); d = s.summary(); "
+            "assert set(d) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples'}; print('ok')" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1000:]
