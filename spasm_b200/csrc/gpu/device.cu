@@ -9,6 +9,7 @@
 
 namespace sb {
 
+static bool g_exiting = false;        /* set by an atexit handler: device_free becomes a no-op */
 static Context g_ctx;
 static Stats g_stats;
 static int g_requested_device = -1;
@@ -49,6 +50,7 @@ Context &ctx()
 	CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
 	unsigned long long keep = ~0ull;
 	CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	atexit([] { g_exiting = true; });      /* registered after the CUDA runtime's own handlers: runs before them */
 	return g_ctx;
 }
 
@@ -74,8 +76,9 @@ static void parallel_memcpy(char *dst, const char *src, size_t bytes, int nthrea
 /* ---- large-block cache (common.cuh) */
 static const size_t BIG_BLOCK = (size_t) 32 << 20;
 struct CachedBlock { void *ptr; size_t bytes; };
-static std::vector<CachedBlock> g_cache;       /* free blocks */
-static std::vector<CachedBlock> g_live_big;    /* blocks handed out from the cache (they may be larger than what was asked for) */
+/* never destroyed: buffers with static storage in other translation units are released at exit, in unspecified order */
+static std::vector<CachedBlock> &g_cache = *new std::vector<CachedBlock>();       /* free blocks */
+static std::vector<CachedBlock> &g_live_big = *new std::vector<CachedBlock>();    /* blocks handed out from the cache (possibly larger than asked) */
 static size_t g_cache_bytes = 0;
 static size_t cache_limit()
 {
@@ -121,6 +124,8 @@ void *device_alloc(size_t bytes)
 
 void device_free(void *ptr, size_t bytes)
 {
+	if (g_exiting)
+		return;                        /* the process is going away: the driver reclaims everything */
 	if (bytes >= BIG_BLOCK) {
 		size_t true_bytes = bytes;
 		for (size_t k = 0; k < g_live_big.size(); k++)
