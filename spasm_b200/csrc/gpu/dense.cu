@@ -13,6 +13,9 @@ namespace sb {
 #define GN 64
 #define GK 32
 
+/* SMALL: |a * b| * 4 < 2^31 (p <= 46337, e.g. the default 42013): four products are summed in 32 bits (full-rate IMAD)
+ * before they join the 64-bit accumulator -- the rank-32 trailing updates of the panels are bound by the multiply-adds */
+template <bool SMALL>
 __global__ void __launch_bounds__(256)
 k_gemm_sub(i32 *__restrict__ C, int ldc, const i32 *__restrict__ A, int lda, const i32 *__restrict__ B, int ldb,
            int M, int N, int K, Zp F, const int *d_K)
@@ -48,6 +51,37 @@ k_gemm_sub(i32 *__restrict__ C, int ldc, const i32 *__restrict__ A, int lda, con
 			Bs[kk][nn] = (gk < K && gn < N) ? B[(size_t) gk * ldb + gn] : 0;
 		}
 		__syncthreads();
+		if (SMALL) {
+#pragma unroll 2
+			for (int kk0 = 0; kk0 < GK; kk0 += 4) {
+				i32 part[4][4];
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+#pragma unroll
+					for (int v = 0; v < 4; v++)
+						part[u][v] = 0;
+#pragma unroll
+				for (int kq = 0; kq < 4; kq++) {
+					i32 a[4], b[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						a[u] = As[kk0 + kq][ty * 4 + u];
+						b[u] = Bs[kk0 + kq][tx * 4 + u];
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++)
+#pragma unroll
+						for (int v = 0; v < 4; v++)
+							part[u][v] += a[u] * b[v];
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+#pragma unroll
+					for (int v = 0; v < 4; v++)
+						acc[u][v] += (i64) part[u][v];
+			}
+			/* delay is astronomically large for such primes (2^63 / p^2 > 2^32 products): no reduction before the end */
+		} else
 #pragma unroll 4
 		for (int kk = 0; kk < GK; kk++) {
 			i32 a[4], b[4];
@@ -100,7 +134,12 @@ void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ld
 		return;
 	}
 	dim3 grid(cdiv(N, GN), cdiv(M, GM));
-	k_gemm_sub<<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
+	/* four products of balanced residues fit 32 bits, and K is far below the delayed-reduction bound */
+	const bool small = F.p <= 46337 && (i64) K < (i64) F.delay;
+	if (small)
+		k_gemm_sub<true><<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
+	else
+		k_gemm_sub<false><<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
 	LAUNCHED(1);
 	KERNEL_CHECK();
 	if (!d_K)
