@@ -1,4 +1,6 @@
 #!/bin/bash
+# Everything the end of a round needs from ONE gpurun call: GPU tests, smoke, bench snapshots (config 2/1/3/5 + the
+# reference arm), then the profiling recipe (tools/profile_run.sh).  tools/summarize_profiles.py turns gpurun_out/ into profiles/.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/final_pytest.txt
