@@ -7,6 +7,10 @@
  */
 #include <string.h>
 #include "spasm.h"
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define SPASM_HAVE_SHANI 1
+#endif
 
 static const u32 K256[64] = {
 	0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
@@ -48,6 +52,75 @@ static void compress(u32 state[8], const u8 *block)
 	state[4] += e; state[5] += f; state[6] += g; state[7] += h;
 }
 
+#ifdef SPASM_HAVE_SHANI
+/* The same compression function with the x86 SHA extensions (sha256rnds2 does two rounds, sha256msg1/msg2 the message
+ * schedule), chosen at run time when the CPU has them: hashing the input file is 40 % of spasm_triplet_load with the
+ * portable code (308 MB/s against ~1.8 GB/s).  State is kept in the (ABEF, CDGH) lane order the instructions expect. */
+__attribute__((target("sha,sse4.1,ssse3")))
+static void compress_shani(u32 state[8], const u8 *data, size_t nblocks)
+{
+	const __m128i bswap = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+	__m128i tmp = _mm_loadu_si128((const __m128i *) &state[0]);          /* DCBA */
+	__m128i st1 = _mm_loadu_si128((const __m128i *) &state[4]);          /* HGFE */
+	tmp = _mm_shuffle_epi32(tmp, 0xB1);                                   /* CDAB */
+	st1 = _mm_shuffle_epi32(st1, 0x1B);                                   /* EFGH */
+	__m128i st0 = _mm_alignr_epi8(tmp, st1, 8);                           /* ABEF */
+	st1 = _mm_blend_epi16(st1, tmp, 0xF0);                                /* CDGH */
+	while (nblocks--) {
+		const __m128i save0 = st0, save1 = st1;
+		__m128i w[4];
+		for (int i = 0; i < 16; i++) {
+			__m128i cur;
+			if (i < 4) {
+				cur = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *) (data + 16 * i)), bswap);
+			} else {
+				/* W[t] = sigma1(W[t-2]) + W[t-7] + sigma0(W[t-15]) + W[t-16], four at a time */
+				__m128i t = _mm_sha256msg1_epu32(w[(i - 4) & 3], w[(i - 3) & 3]);
+				t = _mm_add_epi32(t, _mm_alignr_epi8(w[(i - 1) & 3], w[(i - 2) & 3], 4));
+				cur = _mm_sha256msg2_epu32(t, w[(i - 1) & 3]);
+			}
+			w[i & 3] = cur;
+			__m128i wk = _mm_add_epi32(cur, _mm_loadu_si128((const __m128i *) &K256[4 * i]));
+			st1 = _mm_sha256rnds2_epu32(st1, st0, wk);
+			wk = _mm_shuffle_epi32(wk, 0x0E);
+			st0 = _mm_sha256rnds2_epu32(st0, st1, wk);
+		}
+		st0 = _mm_add_epi32(st0, save0);
+		st1 = _mm_add_epi32(st1, save1);
+		data += 64;
+	}
+	tmp = _mm_shuffle_epi32(st0, 0x1B);                                   /* FEBA */
+	st1 = _mm_shuffle_epi32(st1, 0xB1);                                   /* DCHG */
+	st0 = _mm_blend_epi16(tmp, st1, 0xF0);                                /* DCBA */
+	st1 = _mm_alignr_epi8(st1, tmp, 8);                                   /* HGFE */
+	_mm_storeu_si128((__m128i *) &state[0], st0);
+	_mm_storeu_si128((__m128i *) &state[4], st1);
+}
+
+static int have_shani(void)
+{
+	static int known = -1;
+	if (known < 0) {
+		__builtin_cpu_init();
+		known = __builtin_cpu_supports("sha") && __builtin_cpu_supports("sse4.1") && __builtin_cpu_supports("ssse3");
+	}
+	return known;
+}
+#endif
+
+/* nblocks consecutive 64-byte blocks */
+static void compress_blocks(u32 state[8], const u8 *data, size_t nblocks)
+{
+#ifdef SPASM_HAVE_SHANI
+	if (have_shani()) {
+		compress_shani(state, data, nblocks);
+		return;
+	}
+#endif
+	for (size_t b = 0; b < nblocks; b++)
+		compress(state, data + 64 * b);
+}
+
 void spasm_SHA256_init(spasm_sha256_ctx *c)
 {
 	static const u32 iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
@@ -76,13 +149,14 @@ void spasm_SHA256_update(spasm_sha256_ctx *c, const void *data, size_t len)
 		len -= take;
 		if (c->num < 64)
 			return;
-		compress(c->h, pending);
+		compress_blocks(c->h, pending, 1);
 		c->num = 0;
 	}
-	while (len >= 64) {
-		compress(c->h, in);
-		in += 64;
-		len -= 64;
+	if (len >= 64) {
+		size_t nblocks = len / 64;
+		compress_blocks(c->h, in, nblocks);
+		in += 64 * nblocks;
+		len -= 64 * nblocks;
 	}
 	if (len > 0) {
 		memcpy(pending, in, len);
@@ -97,7 +171,7 @@ void spasm_SHA256_final(u8 *md, spasm_sha256_ctx *c)
 	pending[k++] = 0x80;
 	if (k > 56) {
 		memset(pending + k, 0, 64 - k);
-		compress(c->h, pending);
+		compress_blocks(c->h, pending, 1);
 		k = 0;
 	}
 	memset(pending + k, 0, 56 - k);
@@ -105,7 +179,7 @@ void spasm_SHA256_final(u8 *md, spasm_sha256_ctx *c)
 		pending[56 + b] = (u8) (c->Nh >> (24 - 8 * b));
 		pending[60 + b] = (u8) (c->Nl >> (24 - 8 * b));
 	}
-	compress(c->h, pending);
+	compress_blocks(c->h, pending, 1);
 	c->num = 0;
 	for (int t = 0; t < 8; t++) {
 		md[4 * t] = (u8) (c->h[t] >> 24);

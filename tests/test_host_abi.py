@@ -210,3 +210,26 @@ def test_bench_cli_and_clock_sampler_work_without_a_gpu():
             "assert set(d) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples'}; print('ok')" % root)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1000:]
+
+
+def test_sha256_matches_hashlib_for_every_length_and_chunking(product):
+    """The SHA-256 of the library (portable code or the SHA-NI path picked at run time) against hashlib: every length up
+    to 200 bytes (all padding cases), block boundaries, and random splits of the input over several update calls."""
+    import hashlib
+    import random
+    product.spasm_SHA256_init.argtypes = [C.c_void_p]
+    product.spasm_SHA256_update.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    product.spasm_SHA256_final.argtypes = [C.c_void_p, C.c_void_p]
+    rnd = random.Random(7)
+    for n in list(range(0, 200)) + [1000, 4095, 4096, 4097, 70001]:
+        data = bytes(rnd.getrandbits(8) for _ in range(n))
+        ctx = C.create_string_buffer(256)
+        product.spasm_SHA256_init(ctx)
+        at = 0
+        while at < n:
+            k = rnd.randint(1, 130)
+            product.spasm_SHA256_update(ctx, data[at:at + k], len(data[at:at + k]))
+            at += k
+        out = C.create_string_buffer(32)
+        product.spasm_SHA256_final(out, ctx)
+        assert out.raw == hashlib.sha256(data).digest(), n
