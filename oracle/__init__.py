@@ -132,6 +132,22 @@ def ref():
     return _ref
 
 
+_ref_det = None
+
+
+def ref_det():
+    """The reference's sources with src/spasm_pivots.c compiled without OpenMP (greedy search in row order = the
+    one-thread parity target) and everything else with OpenMP: fast enough for the full-size BASELINE configs."""
+    global _ref_det
+    if _ref_det is None:
+        path = os.path.join(HERE, "_ref", "libspasm_ref_det.so")
+        if not os.path.exists(path):
+            return None
+        from spasm_b200 import abi
+        _ref_det = abi.bind(C.CDLL(path))
+    return _ref_det
+
+
 def reset_rand() -> None:
     """glibc rand() is never seeded by the reference (seed 1); restore that state before each run."""
     _libc.srand(1)

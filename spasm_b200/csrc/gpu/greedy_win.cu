@@ -1,0 +1,555 @@
+/*
+ * Greedy alternating-cycle-free pivot search (reference: src/spasm_pivots.c:146-294), windowed formulation.
+ *
+ * The reference visits the non-pivotal rows in increasing order; row i searches the columns reachable from its
+ * pivotal entries through the pivots committed so far, and takes its first unreached entry on a non-pivotal column.
+ * The result depends on the commit order, so the one-thread reference is the parity target.  What makes it slow on a
+ * GPU is not the searches but the chain of dependent commits (three out of four searching rows of BASELINE config 2
+ * commit, and every commit is seen by a tenth of the later rows).  This file separates the two:
+ *
+ *  A. SEARCH, embarrassingly parallel.  A window of up to Wn candidate rows (rows that still own an entry on a
+ *     non-pivotal column) is searched against the SAME snapshot of the pivots: one CTA per row, visited bitmap in
+ *     shared memory, the pivot row of a column read with one 16..64-byte load from a per-column adjacency record
+ *     (`padj`, rebuilt incrementally) instead of the qinv -> Ap -> Aj chain.  A row whose candidates are all reached
+ *     has failed for good (reachability only grows with the pivot set).  A row with survivors runs its search to
+ *     exhaustion: its visited set is then CLOSED under the snapshot, and it publishes, for every candidate column c
+ *     of the window, the bit "this row reaches c" (R[c], one bit per window row).
+ *
+ *  B. RESOLUTION, sequential but tiny: one CTA walks the surviving rows in increasing order with, per row t, the set
+ *     E[t] of window rows whose searches t INHERITS.  When row t0 commits the pivot (t0, c0), every later row t' that
+ *     reaches c0 -- (R[c0] & E[t']) != 0, or c0 is one of its own candidate entries -- now also reaches whatever t0
+ *     reaches (c0's new out-edges lead to the other entries of row t0, all of them inside t0's closed search, plus
+ *     t0's other candidates):  E[t'] |= E[t0].  Row t's surviving candidates are those c with
+ *     ((R[c] | (C[c] & committed)) & E[t]) == 0, where C[c] = window rows holding c as a candidate; it takes the first
+ *     one in row order (pivots.c:233-237).  This is exactly the reference's journal replay (pivots.c:260-274) with the
+ *     replayed sub-searches replaced by unions of searches that were already run, so the pivots are those of the
+ *     one-thread reference, bit for bit.  A commit costs a few hundred shared-memory cycles instead of a round of
+ *     polling, replaying and re-closing in global memory.
+ *
+ * Rows longer than WIN_MAXC entries, or column counts whose bitmap does not fit shared memory, take the journal
+ * kernels of pivots.cu instead (later rounds on sparse Schur complements).
+ */
+#include <cub/cub.cuh>
+#include "pivots.cuh"
+#include "stats.cuh"
+
+namespace sb {
+
+#define WIN_MAXC 16
+#define WIN_CHUNK 16           /* surviving rows whose vectors are staged in shared memory at a time */
+#define WIN_BFS_THREADS 256
+
+struct WinArgs {
+	int n, m, words;
+	int Wn, W, K;
+	const i64 *Ap;
+	const int *Aj;
+	int *qinv, *pinv;
+	int *padj;                 /* m * K: the other entries of the pivot row of column j; [0] == -2: not pivotal */
+	const int *list;           /* candidate rows after FL / FL on columns, increasing */
+	int nlist;
+	int *pos;                  /* next position in `list` */
+	int *nslots;               /* rows in the current window */
+	int *slotrow, *slotnc;     /* Wn */
+	int *slotcol, *slotvec;    /* Wn * WIN_MAXC: candidate columns in row order, and the vector each of them uses */
+	int *tent;                 /* Wn: row has survivors against the snapshot */
+	int *colmark;              /* m, 0x7f7f7f7f when unused: first window entry holding the column */
+	int *replist, *nrep;       /* entries that own a vector */
+	unsigned *Rvec, *Cvec;     /* (Wn * WIN_MAXC) * W */
+	int *queues;
+	int queue_cap;
+	int *found;
+	unsigned long long *edges;
+};
+
+/* ------------------------------------------------------------------ adjacency records */
+
+template <int K>
+__global__ void k_win_padj_init(int m, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ qinv, int *padj)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m)
+		return;
+	int out[K];
+#pragma unroll
+	for (int k = 0; k < K; k++)
+		out[k] = -1;
+	int I = qinv[j];
+	if (I < 0) {
+		out[0] = -2;
+	} else {
+		int cnt = 0;
+		for (i64 e = Ap[I]; e < Ap[I + 1]; e++) {
+			int c = Aj[e];
+			if (c != j && cnt < K)
+				out[cnt++] = c;
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < K; k += 4)
+		*reinterpret_cast<int4 *>(padj + (size_t) j * K + k) = make_int4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+}
+
+/* rows that are not pivotal and hold an entry on a non-pivotal column */
+__global__ void k_win_flag_rows(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ pinv,
+                                const int *__restrict__ qinv, int *flag)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	int f = 0;
+	if (pinv[i] < 0)
+		for (i64 e = Ap[i]; e < Ap[i + 1] && !f; e++)
+			f = qinv[Aj[e]] < 0;
+	flag[i] = f;
+}
+
+__global__ void k_win_list_rows(int n, const int *__restrict__ flag, const int *__restrict__ off, int *list)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && flag[i])
+		list[off[i]] = i;
+}
+
+/* ------------------------------------------------------------------ window formation (one CTA of 1024 threads) */
+
+__global__ void __launch_bounds__(1024) k_win_form(WinArgs a)
+{
+	typedef cub::BlockScan<int, 1024> Scan;
+	__shared__ typename Scan::TempStorage tmp;
+	__shared__ int s_newpos, s_total;
+	const int tid = threadIdx.x;
+	const int pos = *a.pos;
+	if (pos >= a.nlist) {
+		if (tid == 0)
+			*a.nslots = 0;
+		return;
+	}
+	const int per = (4 * a.Wn + 1023) / 1024;          /* list rows per thread: the chunk holds 4 Wn rows */
+	const int chunk = min(per * 1024, a.nlist - pos);
+	if (tid == 0)
+		s_newpos = pos + chunk;
+	/* which rows of the chunk still own a candidate entry */
+	unsigned mine = 0;
+	int cnt = 0;
+	for (int u = 0; u < per; u++) {
+		int idx = tid * per + u;
+		if (idx < chunk) {
+			int i = a.list[pos + idx];
+			bool f = false;
+			for (i64 e = a.Ap[i]; e < a.Ap[i + 1] && !f; e++)
+				f = a.qinv[a.Aj[e]] < 0;
+			if (f) {
+				mine |= 1u << u;
+				cnt++;
+			}
+		}
+	}
+	int before, total;
+	Scan(tmp).ExclusiveSum(cnt, before, total);
+	__syncthreads();
+	for (int u = 0; u < per; u++)
+		if (mine & (1u << u)) {
+			if (before < a.Wn) {
+				a.slotrow[before] = a.list[pos + tid * per + u];
+				if (before == a.Wn - 1)
+					s_newpos = pos + tid * per + u + 1;
+			}
+			before++;
+		}
+	if (tid == 0)
+		s_total = min(total, a.Wn);
+	__syncthreads();
+	const int nslots = s_total;
+	if (tid == 0) {
+		*a.nslots = nslots;
+		*a.pos = s_newpos;
+		*a.nrep = 0;
+	}
+	/* candidate entries of the window, in row order; the first entry holding a column owns its vectors */
+	for (int b = tid; b < nslots; b += 1024) {
+		int i = a.slotrow[b];
+		int nc = 0;
+		for (i64 e = a.Ap[i]; e < a.Ap[i + 1]; e++) {
+			int c = a.Aj[e];
+			if (a.qinv[c] >= 0)
+				continue;
+			bool dup = false;
+			for (int k = 0; k < nc; k++)
+				dup |= (a.slotcol[b * WIN_MAXC + k] == c);
+			if (dup)
+				continue;              /* a repeated column counts once */
+			a.slotcol[b * WIN_MAXC + nc] = c;
+			atomicMin(&a.colmark[c], b * WIN_MAXC + nc);
+			nc++;
+		}
+		a.slotnc[b] = nc;
+		a.tent[b] = 0;
+	}
+	__threadfence();
+	__syncthreads();
+	for (int b = tid; b < nslots; b += 1024) {
+		int nc = a.slotnc[b];
+		for (int k = 0; k < nc; k++) {
+			int e = b * WIN_MAXC + k;
+			int v = a.colmark[a.slotcol[e]];
+			a.slotvec[e] = v;
+			atomicOr(&a.Cvec[(size_t) v * a.W + (b >> 5)], 1u << (b & 31));
+			if (v == e)
+				a.replist[atomicAdd(a.nrep, 1)] = e;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ phase A: one search per window row */
+
+template <int K>
+__global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
+{
+	extern __shared__ unsigned vis[];
+	__shared__ int s_head, s_tail, s_alive, s_nc;
+	__shared__ int s_cand[WIN_MAXC];
+	const int slot = blockIdx.x, tid = threadIdx.x;
+	if (slot >= *a.nslots)
+		return;
+	int *queue = a.queues + (size_t) slot * a.queue_cap;
+	for (int w = tid; w < a.words; w += WIN_BFS_THREADS)
+		vis[w] = 0;
+	const int row = a.slotrow[slot];
+	const i64 rb = a.Ap[row], re = a.Ap[row + 1];
+	__syncthreads();
+	if (tid == 0) {
+		int tail = 0;
+		for (i64 e = rb; e < re; e++) {
+			int c = a.Aj[e];
+			if (a.qinv[c] < 0)
+				continue;
+			unsigned bit = 1u << (c & 31);
+			if (vis[c >> 5] & bit)
+				continue;
+			vis[c >> 5] |= bit;
+			queue[tail++] = c;
+		}
+		s_head = 0;
+		s_tail = tail;
+		const int nc = a.slotnc[slot];
+		s_nc = nc;
+		s_alive = nc;
+		for (int k = 0; k < nc; k++)
+			s_cand[k] = a.slotcol[slot * WIN_MAXC + k];
+	}
+	__syncthreads();
+	unsigned long long my_edges = 0;
+	for (;;) {
+		const int head = s_head, tail = s_tail, alive = s_alive;
+		__syncthreads();
+		if (head >= tail || alive <= 0)
+			break;
+		const int cnt = min(WIN_BFS_THREADS, tail - head);
+		if (tid < cnt) {
+			const int j = queue[head + tid];
+			int adj[K];
+#pragma unroll
+			for (int k = 0; k < K; k += 4) {
+				int4 v = __ldg(reinterpret_cast<const int4 *>(a.padj + (size_t) j * K + k));
+				adj[k] = v.x; adj[k + 1] = v.y; adj[k + 2] = v.z; adj[k + 3] = v.w;
+			}
+			if (adj[0] != -2) {
+				my_edges += 1;
+#pragma unroll
+				for (int k = 0; k < K; k++) {
+					const int c = adj[k];
+					if (c < 0)
+						continue;
+					my_edges += 1;
+					const unsigned bit = 1u << (c & 31);
+					const unsigned old = atomicOr(&vis[c >> 5], bit);
+					if (!(old & bit))
+						queue[atomicAdd(&s_tail, 1)] = c;
+				}
+			}
+		}
+		__syncthreads();
+		if (tid < 32) {
+			const bool live = tid < s_nc && !(vis[s_cand[tid] >> 5] & (1u << (s_cand[tid] & 31)));
+			const unsigned mask = __ballot_sync(0xffffffffu, live);
+			if (tid == 0) {
+				s_alive = __popc(mask);
+				s_head = head + cnt;
+			}
+		}
+		__syncthreads();
+	}
+	if (my_edges)
+		atomicAdd(a.edges, my_edges);
+	if (s_alive <= 0)
+		return;                                 /* every candidate is reached: failed for good */
+	/* survivors: the search is closed under the snapshot.  Publish which candidate columns of the window it reaches. */
+	if (tid == 0)
+		a.tent[slot] = 1;
+	const int nrep = *a.nrep;
+	const unsigned mybit = 1u << (slot & 31);
+	for (int t = tid; t < nrep; t += WIN_BFS_THREADS) {
+		const int e = a.replist[t];
+		const int c = a.slotcol[e];
+		if (vis[c >> 5] & (1u << (c & 31)))
+			atomicOr(&a.Rvec[(size_t) e * a.W + (slot >> 5)], mybit);
+	}
+}
+
+/* ------------------------------------------------------------------ phase B: ordered resolution, one CTA, blockDim == Wn */
+
+template <int K>
+__global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
+{
+	extern __shared__ unsigned dyn[];
+	const int Wn = a.Wn, W = a.W;
+	unsigned *Et = dyn;                                            /* Et[w * Wn + t]: word w of E[t] */
+	unsigned *chR = Et + (size_t) W * Wn;                          /* WIN_CHUNK * WIN_MAXC * W */
+	unsigned *chC = chR + (size_t) WIN_CHUNK * WIN_MAXC * W;
+	unsigned *taken = chC + (size_t) WIN_CHUNK * WIN_MAXC * W;     /* Wn * WIN_MAXC bits */
+	__shared__ int tl[1024];
+	__shared__ int s_warpcnt[32];
+	__shared__ unsigned s_committed[32], s_reff[32], s_c0[32];
+	__shared__ int s_pick[2], s_T;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nslots = *a.nslots;
+	if (nslots == 0)
+		return;
+	/* surviving rows in increasing order */
+	const bool tentative = tid < nslots && a.tent[tid];
+	const unsigned bal = __ballot_sync(0xffffffffu, tentative);
+	if (lane == 0)
+		s_warpcnt[warp] = __popc(bal);
+	for (int idx = tid; idx < W * Wn; idx += blockDim.x) {
+		int w = idx / Wn, t = idx - w * Wn;
+		Et[idx] = (w == (t >> 5)) ? (1u << (t & 31)) : 0u;
+	}
+	for (int idx = tid; idx < (Wn * WIN_MAXC) / 32; idx += blockDim.x)
+		taken[idx] = 0;
+	if (tid < 32)
+		s_committed[tid] = 0;
+	__syncthreads();
+	{
+		int before = 0;
+		for (int w = 0; w < warp; w++)
+			before += s_warpcnt[w];
+		if (tentative)
+			tl[before + __popc(bal & ((1u << lane) - 1))] = tid;
+		if (tid == blockDim.x - 1)
+			s_T = before + __popc(bal);
+	}
+	__syncthreads();
+	const int T = s_T;
+	int mypick = -1;
+	int iter = 0;                       /* s_pick is double-buffered: a slow warp may still have to read the previous decision */
+	const int my_nc = tid < nslots ? a.slotnc[tid] : 0;
+	(void) my_nc;
+	for (int base = 0; base < T; base += WIN_CHUNK) {
+		/* stage the vectors of the next rows */
+		const int rows_here = min(WIN_CHUNK, T - base);
+		for (int idx = tid; idx < rows_here * WIN_MAXC * W; idx += blockDim.x) {
+			const int r = idx / (WIN_MAXC * W);
+			const int k = (idx / W) % WIN_MAXC;
+			const int w = idx % W;
+			const int b = tl[base + r];
+			if (k < a.slotnc[b]) {
+				const int v = a.slotvec[b * WIN_MAXC + k];
+				chR[idx] = a.Rvec[(size_t) v * W + w];
+				chC[idx] = a.Cvec[(size_t) v * W + w];
+			}
+		}
+		__syncthreads();
+		for (int r = 0; r < rows_here; r++, iter++) {
+			const int b = tl[base + r];
+			if (warp == 0) {
+				const unsigned Ev = lane < W ? Et[lane * Wn + b] : 0u;
+				const unsigned cm = lane < W ? s_committed[lane] : 0u;
+				const int nc = a.slotnc[b];
+				int pick = -1;
+				unsigned reff = 0, c0 = 0;
+				for (int k = 0; k < nc; k++) {
+					const int v = a.slotvec[b * WIN_MAXC + k];
+					if (taken[v >> 5] & (1u << (v & 31)))
+						continue;                               /* became pivotal inside this window */
+					const unsigned cv = lane < W ? chC[(r * WIN_MAXC + k) * W + lane] : 0u;
+					reff = (lane < W ? chR[(r * WIN_MAXC + k) * W + lane] : 0u) | (cv & cm);
+					c0 = cv;
+					if (!__any_sync(0xffffffffu, (reff & Ev) != 0)) {
+						pick = k;
+						break;
+					}
+				}
+				if (pick >= 0 && lane < W) {
+					s_reff[lane] = reff;
+					s_c0[lane] = c0;
+				}
+				if (lane == 0)
+					s_pick[iter & 1] = pick;
+			}
+			__syncthreads();
+			const int pick = s_pick[iter & 1];
+			if (pick < 0)
+				continue;                                       /* uniform: every thread read the same value */
+			/* commit (b, pick): the later rows that reach the new pivot inherit the search of row b */
+			if (tentative && tid > b) {
+				bool hit = (s_c0[tid >> 5] >> (tid & 31)) & 1u;
+				for (int w = 0; w < W && !hit; w++)
+					hit = (Et[w * Wn + tid] & s_reff[w]) != 0;
+				if (hit)
+					for (int w = 0; w < W; w++)
+						Et[w * Wn + tid] |= Et[w * Wn + b];
+			}
+			if (tid == b)
+				mypick = pick;
+			__syncthreads();
+			if (tid == 0) {
+				s_committed[b >> 5] |= 1u << (b & 31);
+				const int v0 = a.slotvec[b * WIN_MAXC + pick];
+				taken[v0 >> 5] |= 1u << (v0 & 31);
+			}
+			if (warp == 0)
+				__syncwarp();
+		}
+		__syncthreads();
+	}
+	/* publish the new pivots and their adjacency records */
+	if (mypick >= 0) {
+		const int row = a.slotrow[tid];
+		const int c0 = a.slotcol[tid * WIN_MAXC + mypick];
+		a.qinv[c0] = row;
+		a.pinv[row] = c0;
+		int cnt = 0;
+		int *rec = a.padj + (size_t) c0 * K;
+		for (i64 e = a.Ap[row]; e < a.Ap[row + 1]; e++) {
+			int c = a.Aj[e];
+			if (c != c0 && cnt < K)
+				rec[cnt++] = c;
+		}
+		for (; cnt < K; cnt++)
+			rec[cnt] = -1;
+		atomicAdd(a.found, 1);
+	}
+}
+
+/* reset what the window used (column marks, vectors) */
+__global__ void k_win_cleanup(WinArgs a)
+{
+	const int nslots = *a.nslots;
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int b = e / WIN_MAXC, k = e - b * WIN_MAXC;
+	if (b >= nslots || k >= a.slotnc[b])
+		return;
+	const int c = a.slotcol[e];
+	a.colmark[c] = 0x7f7f7f7f;
+	if (a.slotvec[e] == e)
+		for (int w = 0; w < a.W; w++) {
+			a.Rvec[(size_t) e * a.W + w] = 0;
+			a.Cvec[(size_t) e * a.W + w] = 0;
+		}
+}
+
+/* ------------------------------------------------------------------ driver */
+
+template <int K>
+static void run_windows(WinArgs &a, size_t bfs_smem, size_t res_smem, int max_windows)
+{
+	cudaStream_t s = ctx().stream;
+	CUDA_CHECK(cudaFuncSetAttribute(k_win_bfs<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bfs_smem));
+	CUDA_CHECK(cudaFuncSetAttribute(k_win_resolve<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) res_smem));
+	k_win_padj_init<K><<<cdiv(a.m, 256), 256, 0, s>>>(a.m, a.Ap, a.Aj, a.qinv, a.padj);
+	LAUNCHED(1);
+	int done = 0;
+	while (done < max_windows) {
+		const int batch = std::min(16, max_windows - done);
+		for (int w = 0; w < batch; w++) {
+			k_win_form<<<1, 1024, 0, s>>>(a);
+			k_win_bfs<K><<<a.Wn, WIN_BFS_THREADS, bfs_smem, s>>>(a);
+			k_win_resolve<K><<<1, a.Wn, res_smem, s>>>(a);
+			k_win_cleanup<<<cdiv((size_t) a.Wn * WIN_MAXC, 256), 256, 0, s>>>(a);
+		}
+		LAUNCHED(4 * batch);
+		KERNEL_CHECK();
+		done += batch;
+		if (fetch(a.pos) >= a.nlist)
+			break;
+	}
+}
+
+/* returns false when the windowed search does not apply (long rows, bitmap too large): the caller takes the journal
+ * kernels.  On success *d_found (device counter) is incremented by the number of new pivots. */
+bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row, int *d_found, unsigned long long *d_edges)
+{
+	cudaStream_t s = ctx().stream;
+	const int n = A.n, m = A.m;
+	static const bool off = getenv("SPASM_B200_GREEDY_JOURNAL") != NULL;
+	if (off || longest_row > WIN_MAXC)
+		return false;
+	WinArgs a;
+	a.n = n;
+	a.m = m;
+	a.words = (m + 31) / 32;
+	const size_t bfs_smem = (size_t) a.words * sizeof(unsigned);
+	if (bfs_smem > 160 * 1024)
+		return false;
+	int Wn = getenv("SPASM_B200_GREEDY_WINDOW") ? atoi(getenv("SPASM_B200_GREEDY_WINDOW")) : 512;
+	Wn = std::max(64, std::min(1024, (Wn + 31) / 32 * 32));
+	a.Wn = Wn;
+	a.W = Wn / 32;
+	a.K = longest_row <= 5 ? 4 : (longest_row <= 9 ? 8 : 16);
+	a.Ap = A.p;
+	a.Aj = A.j;
+	a.qinv = d_qinv;
+	a.pinv = d_pinv;
+	a.found = d_found;
+	a.edges = d_edges;
+	/* candidate rows */
+	DevBuf<int> flag((size_t) n + 1), off_((size_t) n + 1), list((size_t) std::max(n, 1));
+	CUDA_CHECK(cudaMemsetAsync(flag.ptr + n, 0, sizeof(int), s));
+	k_win_flag_rows<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, A.j, d_pinv, d_qinv, flag.ptr);
+	static DevBuf<char> tmp;
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.ptr, off_.ptr, n + 1, s);
+	tmp.ensure(bytes + 16);
+	cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, flag.ptr, off_.ptr, n + 1, s);
+	k_win_list_rows<<<cdiv(n, 256), 256, 0, s>>>(n, flag.ptr, off_.ptr, list.ptr);
+	LAUNCHED(4);
+	a.nlist = fetch(off_.ptr + n);
+	if (a.nlist == 0)
+		return true;
+	a.list = list.ptr;
+	a.queue_cap = m + WIN_MAXC;
+	DevBuf<int> padj((size_t) m * a.K), counters(4), slotrow((size_t) Wn), slotnc((size_t) Wn), slotcol((size_t) Wn * WIN_MAXC),
+	    slotvec((size_t) Wn * WIN_MAXC), tent((size_t) Wn), colmark((size_t) m), replist((size_t) Wn * WIN_MAXC),
+	    queues((size_t) Wn * a.queue_cap);
+	DevBuf<unsigned> Rvec((size_t) Wn * WIN_MAXC * a.W), Cvec((size_t) Wn * WIN_MAXC * a.W);
+	counters.zero(s);
+	colmark.fill_byte(0x7f, s);
+	Rvec.zero(s);
+	Cvec.zero(s);
+	a.padj = padj.ptr;
+	a.pos = counters.ptr + 0;
+	a.nslots = counters.ptr + 1;
+	a.nrep = counters.ptr + 2;
+	a.slotrow = slotrow.ptr;
+	a.slotnc = slotnc.ptr;
+	a.slotcol = slotcol.ptr;
+	a.slotvec = slotvec.ptr;
+	a.tent = tent.ptr;
+	a.colmark = colmark.ptr;
+	a.replist = replist.ptr;
+	a.Rvec = Rvec.ptr;
+	a.Cvec = Cvec.ptr;
+	a.queues = queues.ptr;
+	const size_t res_smem = ((size_t) a.W * Wn + 2 * (size_t) WIN_CHUNK * WIN_MAXC * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
+	const int max_windows = (a.nlist + Wn - 1) / Wn;
+	if (a.K == 4)
+		run_windows<4>(a, bfs_smem, res_smem, max_windows);
+	else if (a.K == 8)
+		run_windows<8>(a, bfs_smem, res_smem, max_windows);
+	else
+		run_windows<16>(a, bfs_smem, res_smem, max_windows);
+	return true;
+}
+
+}  // namespace sb

@@ -739,6 +739,18 @@ __global__ void k_strip_tags(int m, int *qinv)
 
 /* ============================================================ driver */
 
+__global__ void k_longest_row(int n, const i64 *__restrict__ Ap, i64 *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	i64 len = (i < n) ? Ap[i + 1] - Ap[i] : 0;
+	for (int o = 16; o > 0; o >>= 1)
+		len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+	if ((threadIdx.x & 31) == 0 && len > 0)
+		atomicMax((unsigned long long *) out, (unsigned long long) len);
+}
+
+bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row, int *d_found, unsigned long long *d_edges);
+
 PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 {
 	cudaStream_t s = ctx().stream;
@@ -819,23 +831,31 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 		blocks = std::min(blocks, std::max(1, n));
 		/* longest row bounds the extra queue slots used by the initial scatter */
 		a.queue_cap = m + 64;
+		i64 longest = 0;
 		{
 			/* rows longer than 64 entries: enlarge the queues by the longest row */
-			std::vector<i64> hp((size_t) n + 1);
-			A.p.download(hp.data(), (size_t) n + 1, s);
-			sync();
-			i64 longest = 0;
-			for (int i = 0; i < n; i++)
-				longest = std::max(longest, hp[i + 1] - hp[i]);
+			DevBuf<i64> d_longest(1);
+			d_longest.zero(s);
+			k_longest_row<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, d_longest.ptr);
+			LAUNCHED(1);
+			longest = fetch(d_longest.ptr);
 			a.queue_cap = m + (int) longest + 64;
 		}
-		DevBuf<int> journal((size_t) n + 1), status((size_t) n + 1), queues((size_t) blocks * a.queue_cap);
-		DevBuf<unsigned> bitmaps(a.use_smem ? 1 : (size_t) blocks * 2 * a.words);
+		static const bool ordered = getenv("SPASM_B200_GREEDY_ORDERED") != NULL;
+		/* the windowed search (greedy_win.cu) serves short rows; the journal kernels below serve the rest */
+		const bool try_windowed = !ordered && n < GREEDY_TAG;
+		DevBuf<int> journal, status, queues;
+		DevBuf<unsigned> bitmaps;
 		DevBuf<unsigned long long> edges(1);
-		status.zero(s);
 		edges.zero(s);
 		CUDA_CHECK(cudaMemsetAsync(counters.ptr + 3, 0, 5 * sizeof(int), s));
-		static const bool ordered = getenv("SPASM_B200_GREEDY_ORDERED") != NULL;
+		auto journal_buffers = [&]() {
+			journal.alloc((size_t) n + 1);
+			status.alloc((size_t) n + 1);
+			queues.alloc((size_t) blocks * a.queue_cap);
+			bitmaps.alloc(a.use_smem ? 1 : (size_t) blocks * 2 * a.words);
+			status.zero(s);
+		};
 		/* development: run the ordered kernel as well, from the same starting point, and report the differences */
 		static const bool shadow = getenv("SPASM_B200_GREEDY_SHADOW") != NULL;
 		DevBuf<int> pinv0, qinv0;
@@ -846,7 +866,15 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			CUDA_CHECK(cudaMemcpyAsync(qinv0.ptr, d_qinv, (size_t) m * sizeof(int), cudaMemcpyDeviceToDevice, s));
 		}
 		GpuTimer tk;
-		if (ordered || n >= GREEDY_TAG) {
+		bool windowed = false;
+		if (try_windowed) {
+			tk.start();
+			windowed = greedy_windowed(A, d_pinv, d_qinv, longest, counters.ptr + 4, edges.ptr);
+		}
+		if (windowed) {
+			/* done */
+		} else if (ordered || n >= GREEDY_TAG) {
+			journal_buffers();
 			a.journal = journal.ptr;
 			a.npiv = counters.ptr + 3;
 			a.found = counters.ptr + 4;
@@ -858,7 +886,9 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			a.edges = edges.ptr;
 			tk.start();
 			k_greedy<<<blocks, threads, smem, s>>>(a);
+			LAUNCHED(1);
 		} else {
+			journal_buffers();
 			GreedyOooArgs o;
 			o.n = n; o.m = m; o.words = a.words; o.queue_cap = a.queue_cap; o.use_smem = a.use_smem;
 			o.Ap = A.p; o.Aj = A.j; o.qinv = d_qinv; o.pinv = d_pinv;
@@ -886,14 +916,15 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			tk.start();
 			k_greedy_ooo<<<blocks2, threads, smem, s>>>(o);
 			k_strip_tags<<<cdiv(m, 256), 256, 0, s>>>(m, d_qinv);
-			LAUNCHED(1);
+			LAUNCHED(2);
 		}
-		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_greedy += tk.stop_ms();
 		if (shadow && !(ordered || n >= GREEDY_TAG)) {
 			int got = fetch(counters.ptr + 4);
 			DevBuf<int> counters2(8), journal2((size_t) n + 1), status2((size_t) n + 1);
+			if (windowed)
+				journal_buffers();
 			counters2.zero(s);
 			status2.zero(s);
 			a.qinv = qinv0.ptr;
@@ -922,8 +953,8 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 					ndiff++;
 				}
 			if (ndiff)
-				errx(1, "[spasm-b200] greedy pivot search: the out-of-order kernel (%d pivots) and the ordered kernel (%d pivots) differ on %d rows, "
-				        "first on row %d (column %d vs %d)", got, want, ndiff, first, p1[first], p2[first]);
+				errx(1, "[spasm-b200] greedy pivot search: the %s kernel (%d pivots) and the ordered kernel (%d pivots) differ on %d rows, "
+				        "first on row %d (column %d vs %d)", windowed ? "windowed" : "out-of-order", got, want, ndiff, first, p1[first], p2[first]);
 		}
 		out.greedy = fetch(counters.ptr + 4);
 		stats().pub.greedy_edges += (i64) fetch(edges.ptr);
