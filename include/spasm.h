@@ -226,6 +226,26 @@ struct spasm_csr *spasm_transpose(const struct spasm_csr *C, int keep_values);
 void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y);
 void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y);
 
+/* ---------------------- small-grain host verifiers (csrc/host/verify.c) */
+/* Re-entrant, one row at a time; the reference's test programs call them inside their own OpenMP regions to CHECK a
+ * result (tests/echelonize.c:76-113, tests/kernel.c, tests/schur_dense.c).  The echelonization path never does.
+ * reference: src/spasm_scatter.c:7, src/spasm_reach.c:21,:98, src/spasm_triangular.c:21,:65,:109,
+ * src/spasm_permutation.c, src/spasm_submatrix.c:7, src/spasm_kernel.c:133 */
+void spasm_scatter(const struct spasm_csr *A, int i, spasm_ZZp beta, spasm_ZZp *x);
+int spasm_dfs(int i, const struct spasm_csr *G, int top, int *xi, int *pstack, int *marks, const int *pinv);
+int spasm_reach(const struct spasm_csr *A, const struct spasm_csr *B, int k, int l, int *xj, const int *qinv);
+void spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *x, const int *p);
+bool spasm_dense_forward_solve(const struct spasm_csr *U, spasm_ZZp *b, spasm_ZZp *x, const int *q);
+int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_csr *B, int k, int *xj, spasm_ZZp *x, const int *qinv);
+void spasm_pvec(const int *p, const spasm_ZZp *b, spasm_ZZp *x, int n);
+void spasm_ipvec(const int *p, const spasm_ZZp *b, spasm_ZZp *x, int n);
+int *spasm_pinv(int const *p, int n);
+struct spasm_csr *spasm_permute(const struct spasm_csr *A, const int *p, const int *qinv, int with_values);
+int *spasm_random_permutation(int n);
+void spasm_range_pvec(int *x, int a, int b, int *p);
+struct spasm_csr *spasm_submatrix(const struct spasm_csr *A, int r_0, int r_1, int c_0, int c_1, int with_values);
+struct spasm_csr *spasm_kernel_from_rref(const struct spasm_csr *R, const int *qinv);
+
 /* ------------------------------------------------ the hot path (on B200) */
 
 /* reference: src/spasm_pivots.c:369 */

@@ -67,6 +67,8 @@ def build(with_ref: bool | None = None) -> None:
         if os.path.exists(os.path.join(os.path.dirname(HERE), "spasm_b200", "lib", "libspasm_b200.so")):
             # the reference's unmodified tools linked against the product library
             subprocess.run(["make", "-s", "-C", HERE, "b200_tools"], check=True)
+            # ... and its unmodified test programs (tests/test_reference_tests.py)
+            subprocess.run(["make", "-s", "-C", HERE, "b200_tests"], check=True)
 
 
 def lib() -> C.CDLL:

@@ -1,0 +1,111 @@
+"""The reference's OWN test programs (tests/*.c of /root/reference), compiled where they lie against include/spasm.h
+and linked against libspasm_b200.so by `make -C oracle b200_tests` (in the build container; the binaries travel to
+the GPU box inside oracle/_ref/).  They are run the way tests/CMakeLists.txt:20-26,46-61 runs them: fixture on stdin,
+`--modulus P`, failure = non-zero exit or "not ok" on stdout.
+
+CPU tier: the programs that only exercise host code of the boundary (field, PRNG, SHA-256, permutations, transpose,
+spmv, sub-matrix, the one-row triangular solves).  GPU tier: echelonize, kernel, schur, schur_dense,
+dense_rref_ffpack, sparse_utsolve -- they call spasm_echelonize & co. (CUDA) and CHECK the result with the host
+verifiers of csrc/host/verify.c, i.e. with the reference's own row-by-row arithmetic.
+
+The known answers in tests/golden/expected/ are the reference's tests/Expected/{prng,hash,gaxpy.1,submatrix.1}."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from spasm_b200 import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref")
+EXPECTED = os.path.join(ROOT, "tests", "golden", "expected")
+MODULI = (3, 257, 65537, 67108859, 189812507, 4294967291)       # tests/CMakeLists.txt:46-61
+FIXTURES = None
+
+
+def fixture_names():
+    global FIXTURES
+    if FIXTURES is None:
+        f = np.load(os.path.join(util.GOLDEN_DIR, "fixtures.npz"))
+        FIXTURES = sorted({k.rsplit(".", 1)[0] for k in f.files})
+    return FIXTURES
+
+
+def sms_of(name: str) -> bytes:
+    f = np.load(os.path.join(util.GOLDEN_DIR, "fixtures.npz"))
+    n, m = (int(v) for v in f[f"{name}.shape"])
+    return synthetic.Triplets(n, m, 0, f[f"{name}.i"], f[f"{name}.j"], f[f"{name}.x"], name).to_sms()
+
+
+def run(prog: str, *args, stdin: bytes = b"", timeout=120):
+    path = os.path.join(BIN, "b200_test_" + prog)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/b200_test_* not built (make -C oracle b200_tests needs /root/reference)")
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    return subprocess.run([path, *args], input=stdin, capture_output=True, env=env, timeout=timeout)
+
+
+def check(r, what):
+    assert r.returncode == 0, f"{what}: exit {r.returncode}\n{r.stdout[-600:].decode(errors='replace')}\n{r.stderr[-600:].decode(errors='replace')}"
+    assert b"not ok" not in r.stdout, f"{what}:\n{r.stdout[-800:].decode(errors='replace')}"
+
+
+# ---------------------------------------------------------------- host-only programs (no GPU)
+
+def test_GFp():
+    check(run("GFp", timeout=600), "GFp")
+
+
+@pytest.mark.parametrize("prog,expected", [("prng", "prng"), ("sha", "hash")])
+def test_known_answer_programs(prog, expected):
+    r = run(prog)
+    check(r, prog)
+    with open(os.path.join(EXPECTED, expected), "rb") as f:
+        assert r.stdout == f.read()
+
+
+def test_vec_perm():
+    check(run("vec_perm"), "vec_perm")
+
+
+@pytest.mark.parametrize("fixture", ["small", "upper_trapeze"])
+def test_mat_perm(fixture):
+    check(run("mat_perm", "--modulus", "65537", stdin=sms_of(fixture)), "mat_perm " + fixture)
+
+
+def test_transpose_on_every_fixture():
+    for name in fixture_names():
+        check(run("transpose", "--modulus", "257", stdin=sms_of(name)), "transpose " + name)
+
+
+@pytest.mark.parametrize("prog,fixture,expected", [("spmv", "m1", "gaxpy.1"), ("submatrix", "singular", "submatrix.1")])
+def test_expected_output_programs(prog, fixture, expected):
+    r = run(prog, stdin=sms_of(fixture))
+    check(r, prog)
+    with open(os.path.join(EXPECTED, expected), "rb") as f:
+        assert r.stdout == f.read()
+
+
+@pytest.mark.parametrize("prog", ["dense_usolve", "sparse_usolve"])
+def test_upper_triangular_solves(prog):
+    for name in ("u1", "upper_trapeze"):
+        for p in MODULI:
+            check(run(prog, "--modulus", str(p), stdin=sms_of(name)), f"{prog} {name} mod {p}")
+
+
+# ---------------------------------------------------------------- programs that run the CUDA path
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", ["echelonize", "kernel", "schur", "schur_dense", "dense_rref_ffpack", "sparse_utsolve"])
+def test_reference_program_on_every_fixture_and_modulus(prog):
+    """tests/CMakeLists.txt spasm_run_tests_mod: 32 fixtures x 6 moduli"""
+    failures = []
+    for name in fixture_names():
+        sms = sms_of(name)
+        for p in MODULI:
+            r = run(prog, "--modulus", str(p), stdin=sms, timeout=300)
+            if r.returncode != 0 or b"not ok" in r.stdout:
+                failures.append((name, p, r.returncode, r.stdout[-200:], r.stderr[-300:]))
+    assert not failures, f"{len(failures)} failing runs, first: {failures[:3]}"
