@@ -90,6 +90,67 @@ static struct spasm_csr *pieces_to_host(const std::vector<HostPiece> &pieces, in
 	return H;
 }
 
+/*
+ * Multi-GPU exchange of result rows (spasm_rref shards the rows of U, spasm_kernel the non-pivotal
+ * columns; reference loops: src/spasm_rref.c:44-56, src/spasm_kernel.c:42-51 are independent-iteration).
+ * Every rank computed the pieces of ITS contiguous slice; on return `pieces` holds the pieces of every rank in rank
+ * order (= row order of the result), in HBM.  One all-gather of the piece sizes, then one NCCL group of broadcasts,
+ * each piece from its owner (variable lengths, no padding).
+ */
+#define MAX_PIECES_PER_RANK 255
+static void exchange_pieces(std::vector<HostPiece> &pieces)
+{
+	const int world = comm_world(), me = comm_rank();
+	if (world == 1)
+		return;
+	cudaStream_t s = ctx().stream;
+	if (pieces.size() > MAX_PIECES_PER_RANK)
+		errx(1, "[spasm-b200] internal: too many result batches on one rank");
+	const size_t per = 2 * MAX_PIECES_PER_RANK + 2;
+	std::vector<i64> meta(per * world, 0);
+	i64 *mine = meta.data() + per * me;
+	mine[0] = (i64) pieces.size();
+	for (size_t k = 0; k < pieces.size(); k++) {
+		mine[1 + 2 * k] = pieces[k].rows;
+		mine[2 + 2 * k] = pieces[k].nnz;
+	}
+	DevBuf<i64> d_meta;
+	d_meta.upload(meta.data(), meta.size(), s);
+	comm_allgather_bytes(d_meta.ptr, per * sizeof(i64));
+	d_meta.download(meta.data(), meta.size(), s);
+	sync();
+	std::vector<HostPiece> all;
+	for (int r = 0; r < world; r++) {
+		const i64 *mr = meta.data() + per * r;
+		for (i64 k = 0; k < mr[0]; k++) {
+			if (r == me) {
+				all.push_back(std::move(pieces[k]));
+			} else {
+				all.emplace_back();
+				HostPiece &pc = all.back();
+				pc.rows = (int) mr[1 + 2 * k];
+				pc.nnz = mr[2 + 2 * k];
+				pc.p.alloc((size_t) pc.rows + 1);
+				pc.j.alloc((size_t) std::max<i64>(pc.nnz, 1));
+				pc.x.alloc((size_t) std::max<i64>(pc.nnz, 1));
+			}
+		}
+	}
+	comm_group_begin();
+	size_t at = 0;
+	for (int r = 0; r < world; r++) {
+		const i64 *mr = meta.data() + per * r;
+		for (i64 k = 0; k < mr[0]; k++, at++) {
+			HostPiece &pc = all[at];
+			comm_bcast_bytes(pc.p.ptr, ((size_t) pc.rows + 1) * sizeof(i64), r);
+			comm_bcast_bytes(pc.j.ptr, (size_t) pc.nnz * sizeof(int), r);
+			comm_bcast_bytes(pc.x.ptr, (size_t) pc.nnz * sizeof(i32), r);
+		}
+	}
+	comm_group_end();
+	pieces = std::move(all);
+}
+
 static void store_dense(void *S, spasm_datatype datatype, const std::vector<i32> &host, int rows, int ld, int Sm)
 {
 	for (int r = 0; r < rows; r++)
@@ -335,8 +396,11 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 		pivcol[i] = U->j[U->p[i]];
 	const int cap = panel_capacity(m, 64.0);
 	std::vector<HostPiece> pieces;
-	for (int done = 0; done < n; done += cap) {
-		int R = std::min(cap, n - done);
+	/* several ranks: each one reduces a contiguous slice of the rows (they are independent given U, rref.c:44-56) */
+	int chunk, slice_begin, slice_end;
+	comm_slice(n, &chunk, &slice_begin, &slice_end);
+	for (int done = slice_begin; done < slice_end; done += cap) {
+		int R = std::min(cap, slice_end - done);
 		std::vector<int> rows(R);
 		for (int r = 0; r < R; r++)
 			rows[r] = done + r;
@@ -356,6 +420,8 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 		piece_download(Sp, Sj, Sx, R, nnz, pieces.back());
 		lap("panel -> sparse rows");
 	}
+	exchange_pieces(pieces);
+	lap("exchange");
 	struct spasm_csr *Rm = pieces_to_host(pieces, n, m, spasm_get_prime(U));
 	lap("download");
 	for (int j = 0; j < m; j++)
@@ -399,8 +465,11 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact)
 	std::vector<HostPiece> pieces;
 	std::vector<int> colslot((size_t) std::max(m, 1));
 	Panel P;
-	for (size_t done = 0; done < freecols.size(); done += cap) {
-		int R = (int) std::min<size_t>(cap, freecols.size() - done);
+	/* several ranks: each one takes a contiguous slice of the non-pivotal columns (kernel.c:42-51) */
+	int chunk, slice_begin, slice_end;
+	comm_slice((int) freecols.size(), &chunk, &slice_begin, &slice_end);
+	for (size_t done = (size_t) slice_begin; done < (size_t) slice_end; done += cap) {
+		int R = (int) std::min<size_t>(cap, (size_t) slice_end - done);
 		std::fill(colslot.begin(), colslot.end(), -1);
 		for (int r = 0; r < R; r++)
 			colslot[freecols[done + r]] = r;
@@ -421,6 +490,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact)
 		pieces.emplace_back();
 		piece_download(Sp, Sj, Sx, R, nnz, pieces.back());
 	}
+	exchange_pieces(pieces);
 	struct spasm_csr *K = pieces_to_host(pieces, m - n, m, spasm_get_prime(U));
 	spasm_human_format(spasm_nnz(K), hnnz);
 	LOG("[kernel] done. NNZ(K) = %s\n", hnnz);

@@ -29,6 +29,9 @@ static struct {
 	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 	ncclComm_t comm = nullptr;
 	int rank = 0, world = 1;
@@ -48,7 +51,10 @@ static void nccl_load()
 	*(void **) &g_nccl.CommDestroy = dlsym(g_nccl.handle, "ncclCommDestroy");
 	*(void **) &g_nccl.AllGather = dlsym(g_nccl.handle, "ncclAllGather");
 	*(void **) &g_nccl.GetErrorString = dlsym(g_nccl.handle, "ncclGetErrorString");
-	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather)
+	*(void **) &g_nccl.Broadcast = dlsym(g_nccl.handle, "ncclBroadcast");
+	*(void **) &g_nccl.GroupStart = dlsym(g_nccl.handle, "ncclGroupStart");
+	*(void **) &g_nccl.GroupEnd = dlsym(g_nccl.handle, "ncclGroupEnd");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
 		errx(1, "[spasm-b200] NCCL library lacks the expected entry points");
 }
 
@@ -80,6 +86,27 @@ void comm_allgather_rows(i32 *B, int chunk, int ld)
 	size_t count = (size_t) chunk * ld;
 	NCCL_CHECK(g_nccl.AllGather(B + (size_t) g_nccl.rank * count, B, count, ncclInt32, g_nccl.comm, ctx().stream));
 	stats().pub.nccl_bytes += (i64) count * 4 * (g_nccl.world - 1);
+}
+
+/* in-place all-gather of `bytes` bytes per rank (rank r's part at offset r * bytes) */
+void comm_allgather_bytes(void *buf, size_t bytes)
+{
+	if (g_nccl.world == 1)
+		return;
+	NCCL_CHECK(g_nccl.AllGather((char *) buf + (size_t) g_nccl.rank * bytes, buf, bytes, 0 /* ncclInt8 */, g_nccl.comm, ctx().stream));
+	stats().pub.nccl_bytes += (i64) bytes * (g_nccl.world - 1);
+}
+
+/* broadcasts of variable-length pieces, fused into one NCCL group by the caller (comm_group_begin / _end) */
+void comm_group_begin() { if (g_nccl.world > 1) NCCL_CHECK(g_nccl.GroupStart()); }
+void comm_group_end() { if (g_nccl.world > 1) NCCL_CHECK(g_nccl.GroupEnd()); }
+void comm_bcast_bytes(void *buf, size_t bytes, int root)
+{
+	if (g_nccl.world == 1 || bytes == 0)
+		return;
+	NCCL_CHECK(g_nccl.Broadcast(buf, buf, bytes, 0 /* ncclInt8 */, root, g_nccl.comm, ctx().stream));
+	if (root != g_nccl.rank)
+		stats().pub.nccl_bytes += (i64) bytes;
 }
 
 }  // namespace sb

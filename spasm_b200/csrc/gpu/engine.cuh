@@ -66,5 +66,9 @@ int comm_world();
 int comm_rank();
 void comm_slice(int total, int *chunk, int *begin, int *end);
 void comm_allgather_rows(i32 *B, int chunk, int ld);
+void comm_allgather_bytes(void *buf, size_t bytes);
+void comm_group_begin();
+void comm_group_end();
+void comm_bcast_bytes(void *buf, size_t bytes, int root);
 
 }  // namespace sb

@@ -36,8 +36,9 @@
 namespace sb {
 
 #define WIN_MAXC 16
-#define WIN_CHUNK 16           /* surviving rows whose vectors are staged in shared memory at a time */
+#define WIN_ECAP 256           /* candidate entries whose vectors are staged in shared memory at a time (phase B) */
 #define WIN_BFS_THREADS 256
+#define WIN_RING 4096          /* frontier ring in shared memory (phase A); the global queue holds everything */
 
 struct WinArgs {
 	int n, m, words;
@@ -47,10 +48,11 @@ struct WinArgs {
 	int *qinv, *pinv;
 	int *padj;                 /* m * K: the other entries of the pivot row of column j; [0] == -2: not pivotal */
 	const int *list;           /* candidate rows after FL / FL on columns, increasing */
+	const int *lrow;           /* nlist * WIN_MAXC: their entries, padded with -1 */
 	int nlist;
 	int *pos;                  /* next position in `list` */
 	int *nslots;               /* rows in the current window */
-	int *slotrow, *slotnc;     /* Wn */
+	int *slotrow, *slotlidx, *slotnc;   /* Wn: row, its index in `list`, number of candidate entries */
 	int *slotcol, *slotvec;    /* Wn * WIN_MAXC: candidate columns in row order, and the vector each of them uses */
 	int *tent;                 /* Wn: row has survivors against the snapshot */
 	int *colmark;              /* m, 0x7f7f7f7f when unused: first window entry holding the column */
@@ -104,11 +106,47 @@ __global__ void k_win_flag_rows(int n, const i64 *__restrict__ Ap, const int *__
 	flag[i] = f;
 }
 
-__global__ void k_win_list_rows(int n, const int *__restrict__ flag, const int *__restrict__ off, int *list)
+/* the list of candidate rows and a padded copy of their entries (distinct columns, row order): the window kernels
+ * read a row with four 16-byte loads instead of walking Ap -> Aj */
+__global__ void k_win_list_rows(int n, const int *__restrict__ flag, const int *__restrict__ off, const i64 *__restrict__ Ap,
+                                const int *__restrict__ Aj, int *list, int *lrow)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n && flag[i])
-		list[off[i]] = i;
+	if (i >= n || !flag[i])
+		return;
+	const int t = off[i];
+	list[t] = i;
+	int ent[WIN_MAXC];
+#pragma unroll
+	for (int k = 0; k < WIN_MAXC; k++)
+		ent[k] = -1;
+	int cnt = 0;
+	for (i64 e = Ap[i]; e < Ap[i + 1]; e++) {
+		const int c = Aj[e];
+		bool dup = false;
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++)
+			dup |= (ent[k] == c);
+		if (!dup) {                        /* a repeated column counts once */
+#pragma unroll
+			for (int k = 0; k < WIN_MAXC; k++)
+				if (k == cnt)
+					ent[k] = c;
+			cnt++;
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < WIN_MAXC; k += 4)
+		*reinterpret_cast<int4 *>(lrow + (size_t) t * WIN_MAXC + k) = make_int4(ent[k], ent[k + 1], ent[k + 2], ent[k + 3]);
+}
+
+__device__ __forceinline__ void load_row16(const int *lrow, int lidx, int (&ent)[WIN_MAXC])
+{
+#pragma unroll
+	for (int k = 0; k < WIN_MAXC; k += 4) {
+		const int4 v = *reinterpret_cast<const int4 *>(lrow + (size_t) lidx * WIN_MAXC + k);
+		ent[k] = v.x; ent[k + 1] = v.y; ent[k + 2] = v.z; ent[k + 3] = v.w;
+	}
 }
 
 /* ------------------------------------------------------------------ window formation (one CTA of 1024 threads) */
@@ -133,12 +171,18 @@ __global__ void __launch_bounds__(1024) k_win_form(WinArgs a)
 	unsigned mine = 0;
 	int cnt = 0;
 	for (int u = 0; u < per; u++) {
-		int idx = tid * per + u;
+		const int idx = tid * per + u;
 		if (idx < chunk) {
-			int i = a.list[pos + idx];
+			int ent[WIN_MAXC];
+			load_row16(a.lrow, pos + idx, ent);
+			int q[WIN_MAXC];
+#pragma unroll
+			for (int k = 0; k < WIN_MAXC; k++)
+				q[k] = ent[k] >= 0 ? a.qinv[ent[k]] : 0;
 			bool f = false;
-			for (i64 e = a.Ap[i]; e < a.Ap[i + 1] && !f; e++)
-				f = a.qinv[a.Aj[e]] < 0;
+#pragma unroll
+			for (int k = 0; k < WIN_MAXC; k++)
+				f |= q[k] < 0;
 			if (f) {
 				mine |= 1u << u;
 				cnt++;
@@ -151,7 +195,7 @@ __global__ void __launch_bounds__(1024) k_win_form(WinArgs a)
 	for (int u = 0; u < per; u++)
 		if (mine & (1u << u)) {
 			if (before < a.Wn) {
-				a.slotrow[before] = a.list[pos + tid * per + u];
+				a.slotlidx[before] = pos + tid * per + u;
 				if (before == a.Wn - 1)
 					s_newpos = pos + tid * per + u + 1;
 			}
@@ -168,31 +212,32 @@ __global__ void __launch_bounds__(1024) k_win_form(WinArgs a)
 	}
 	/* candidate entries of the window, in row order; the first entry holding a column owns its vectors */
 	for (int b = tid; b < nslots; b += 1024) {
-		int i = a.slotrow[b];
+		const int lidx = a.slotlidx[b];
+		int ent[WIN_MAXC];
+		load_row16(a.lrow, lidx, ent);
+		int q[WIN_MAXC];
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++)
+			q[k] = ent[k] >= 0 ? a.qinv[ent[k]] : 0;
 		int nc = 0;
-		for (i64 e = a.Ap[i]; e < a.Ap[i + 1]; e++) {
-			int c = a.Aj[e];
-			if (a.qinv[c] >= 0)
-				continue;
-			bool dup = false;
-			for (int k = 0; k < nc; k++)
-				dup |= (a.slotcol[b * WIN_MAXC + k] == c);
-			if (dup)
-				continue;              /* a repeated column counts once */
-			a.slotcol[b * WIN_MAXC + nc] = c;
-			atomicMin(&a.colmark[c], b * WIN_MAXC + nc);
-			nc++;
-		}
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++)
+			if (q[k] < 0) {
+				a.slotcol[b * WIN_MAXC + nc] = ent[k];
+				atomicMin(&a.colmark[ent[k]], b * WIN_MAXC + nc);
+				nc++;
+			}
 		a.slotnc[b] = nc;
+		a.slotrow[b] = a.list[lidx];
 		a.tent[b] = 0;
 	}
 	__threadfence();
 	__syncthreads();
 	for (int b = tid; b < nslots; b += 1024) {
-		int nc = a.slotnc[b];
+		const int nc = a.slotnc[b];
 		for (int k = 0; k < nc; k++) {
-			int e = b * WIN_MAXC + k;
-			int v = a.colmark[a.slotcol[e]];
+			const int e = b * WIN_MAXC + k;
+			const int v = a.colmark[a.slotcol[e]];
 			a.slotvec[e] = v;
 			atomicOr(&a.Cvec[(size_t) v * a.W + (b >> 5)], 1u << (b & 31));
 			if (v == e)
@@ -207,51 +252,60 @@ template <int K>
 __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 {
 	extern __shared__ unsigned vis[];
-	__shared__ int s_head, s_tail, s_alive, s_nc;
+	__shared__ int s_tail, s_nc;
+	__shared__ int s_alive[2];
 	__shared__ int s_cand[WIN_MAXC];
+	__shared__ int ring[WIN_RING];
 	const int slot = blockIdx.x, tid = threadIdx.x;
 	if (slot >= *a.nslots)
 		return;
 	int *queue = a.queues + (size_t) slot * a.queue_cap;
 	for (int w = tid; w < a.words; w += WIN_BFS_THREADS)
 		vis[w] = 0;
-	const int row = a.slotrow[slot];
-	const i64 rb = a.Ap[row], re = a.Ap[row + 1];
 	__syncthreads();
 	if (tid == 0) {
-		int tail = 0;
-		for (i64 e = rb; e < re; e++) {
-			int c = a.Aj[e];
-			if (a.qinv[c] < 0)
+		int ent[WIN_MAXC];
+		load_row16(a.lrow, a.slotlidx[slot], ent);
+		int q[WIN_MAXC];
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++)
+			q[k] = ent[k] >= 0 ? a.qinv[ent[k]] : -1;
+		int tail = 0, nc = 0;
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++) {
+			if (ent[k] < 0)
 				continue;
-			unsigned bit = 1u << (c & 31);
-			if (vis[c >> 5] & bit)
-				continue;
-			vis[c >> 5] |= bit;
-			queue[tail++] = c;
+			if (q[k] >= 0) {                    /* pivotal at the snapshot: a source of the search */
+				vis[ent[k] >> 5] |= 1u << (ent[k] & 31);
+				ring[tail] = ent[k];
+				queue[tail++] = ent[k];
+			} else {
+				s_cand[nc++] = ent[k];
+			}
 		}
-		s_head = 0;
 		s_tail = tail;
-		const int nc = a.slotnc[slot];
 		s_nc = nc;
-		s_alive = nc;
-		for (int k = 0; k < nc; k++)
-			s_cand[k] = a.slotcol[slot * WIN_MAXC + k];
+		s_alive[0] = nc;
+		s_alive[1] = nc;
 	}
 	__syncthreads();
 	unsigned long long my_edges = 0;
-	for (;;) {
-		const int head = s_head, tail = s_tail, alive = s_alive;
-		__syncthreads();
+	int head = 0;
+	int tail = s_tail, alive = s_alive[0];
+	for (int iter = 0;; iter++) {
+		/* one slice of the frontier per iteration.  head is replicated; the tail and the survivor count are read
+		 * between two barriers (nobody pushes then), the count lags by one slice and is double-buffered, so every
+		 * thread takes the same decisions */
 		if (head >= tail || alive <= 0)
 			break;
 		const int cnt = min(WIN_BFS_THREADS, tail - head);
+		const bool in_ring = tail - head <= WIN_RING;
 		if (tid < cnt) {
-			const int j = queue[head + tid];
+			const int j = in_ring ? ring[(head + tid) & (WIN_RING - 1)] : queue[head + tid];
 			int adj[K];
 #pragma unroll
 			for (int k = 0; k < K; k += 4) {
-				int4 v = __ldg(reinterpret_cast<const int4 *>(a.padj + (size_t) j * K + k));
+				const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) j * K + k);
 				adj[k] = v.x; adj[k + 1] = v.y; adj[k + 2] = v.z; adj[k + 3] = v.w;
 			}
 			if (adj[0] != -2) {
@@ -264,27 +318,44 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 					my_edges += 1;
 					const unsigned bit = 1u << (c & 31);
 					const unsigned old = atomicOr(&vis[c >> 5], bit);
-					if (!(old & bit))
-						queue[atomicAdd(&s_tail, 1)] = c;
+					if (!(old & bit)) {
+						const int at = atomicAdd(&s_tail, 1);
+						ring[at & (WIN_RING - 1)] = c;
+						queue[at] = c;
+					}
 				}
 			}
-		}
-		__syncthreads();
-		if (tid < 32) {
-			const bool live = tid < s_nc && !(vis[s_cand[tid] >> 5] & (1u << (s_cand[tid] & 31)));
+		} else if (cnt <= WIN_BFS_THREADS - 32 && tid >= WIN_BFS_THREADS - 32) {
+			/* the last warp is rarely busy with the frontier: it recounts the survivors (marks of the earlier slices) */
+			const int l = tid - (WIN_BFS_THREADS - 32);
+			const bool live = l < s_nc && !(vis[s_cand[l] >> 5] & (1u << (s_cand[l] & 31)));
 			const unsigned mask = __ballot_sync(0xffffffffu, live);
-			if (tid == 0) {
-				s_alive = __popc(mask);
-				s_head = head + cnt;
-			}
+			if (l == 0)
+				s_alive[(iter + 1) & 1] = __popc(mask);
 		}
+		if (cnt > WIN_BFS_THREADS - 32 && tid == 0)
+			s_alive[(iter + 1) & 1] = alive;      /* full slice: carry the count over, recount later */
+		head += cnt;
+		__syncthreads();
+		tail = s_tail;
+		alive = s_alive[(iter + 1) & 1];
 		__syncthreads();
 	}
+	__syncthreads();
 	if (my_edges)
 		atomicAdd(a.edges, my_edges);
-	if (s_alive <= 0)
+	/* final recount with every mark in place */
+	if (tid < 32) {
+		const bool live = tid < s_nc && !(vis[s_cand[tid] >> 5] & (1u << (s_cand[tid] & 31)));
+		const unsigned mask = __ballot_sync(0xffffffffu, live);
+		if (tid == 0)
+			s_alive[0] = __popc(mask);
+	}
+	__syncthreads();
+	if (s_alive[0] <= 0)
 		return;                                 /* every candidate is reached: failed for good */
-	/* survivors: the search is closed under the snapshot.  Publish which candidate columns of the window it reaches. */
+	/* survivors.  The loop above stops early only when no candidate is left, so the search ran to exhaustion: it is
+	 * closed under the snapshot.  Publish which candidate columns of the window it reaches. */
 	if (tid == 0)
 		a.tent[slot] = 1;
 	const int nrep = *a.nrep;
@@ -305,24 +376,26 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 	extern __shared__ unsigned dyn[];
 	const int Wn = a.Wn, W = a.W;
 	unsigned *Et = dyn;                                            /* Et[w * Wn + t]: word w of E[t] */
-	unsigned *chR = Et + (size_t) W * Wn;                          /* WIN_CHUNK * WIN_MAXC * W */
-	unsigned *chC = chR + (size_t) WIN_CHUNK * WIN_MAXC * W;
-	unsigned *taken = chC + (size_t) WIN_CHUNK * WIN_MAXC * W;     /* Wn * WIN_MAXC bits */
-	__shared__ int tl[1024];
+	unsigned *chR = Et + (size_t) W * Wn;                          /* WIN_ECAP * W */
+	unsigned *chC = chR + (size_t) WIN_ECAP * W;
+	unsigned *taken = chC + (size_t) WIN_ECAP * W;                 /* Wn * WIN_MAXC bits */
+	__shared__ int tl[1024];                                       /* surviving rows, increasing */
+	__shared__ unsigned char tnc[1024];                            /* their number of candidate entries */
+	__shared__ int ch_vec[WIN_ECAP];
+	__shared__ int ch_off[WIN_ECAP + 1];
 	__shared__ int s_warpcnt[32];
 	__shared__ unsigned s_committed[32], s_reff[32], s_c0[32];
-	__shared__ int s_pick[2], s_T;
+	__shared__ int s_pick[2], s_T, s_rows;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nslots = *a.nslots;
 	if (nslots == 0)
 		return;
-	/* surviving rows in increasing order */
 	const bool tentative = tid < nslots && a.tent[tid];
 	const unsigned bal = __ballot_sync(0xffffffffu, tentative);
 	if (lane == 0)
 		s_warpcnt[warp] = __popc(bal);
 	for (int idx = tid; idx < W * Wn; idx += blockDim.x) {
-		int w = idx / Wn, t = idx - w * Wn;
+		const int w = idx / Wn, t = idx - w * Wn;
 		Et[idx] = (w == (t >> 5)) ? (1u << (t & 31)) : 0u;
 	}
 	for (int idx = tid; idx < (Wn * WIN_MAXC) / 32; idx += blockDim.x)
@@ -334,8 +407,11 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 		int before = 0;
 		for (int w = 0; w < warp; w++)
 			before += s_warpcnt[w];
-		if (tentative)
-			tl[before + __popc(bal & ((1u << lane) - 1))] = tid;
+		if (tentative) {
+			const int t = before + __popc(bal & ((1u << lane) - 1));
+			tl[t] = tid;
+			tnc[t] = (unsigned char) a.slotnc[tid];
+		}
 		if (tid == blockDim.x - 1)
 			s_T = before + __popc(bal);
 	}
@@ -343,37 +419,49 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 	const int T = s_T;
 	int mypick = -1;
 	int iter = 0;                       /* s_pick is double-buffered: a slow warp may still have to read the previous decision */
-	const int my_nc = tid < nslots ? a.slotnc[tid] : 0;
-	(void) my_nc;
-	for (int base = 0; base < T; base += WIN_CHUNK) {
-		/* stage the vectors of the next rows */
-		const int rows_here = min(WIN_CHUNK, T - base);
-		for (int idx = tid; idx < rows_here * WIN_MAXC * W; idx += blockDim.x) {
-			const int r = idx / (WIN_MAXC * W);
-			const int k = (idx / W) % WIN_MAXC;
-			const int w = idx % W;
-			const int b = tl[base + r];
-			if (k < a.slotnc[b]) {
-				const int v = a.slotvec[b * WIN_MAXC + k];
-				chR[idx] = a.Rvec[(size_t) v * W + w];
-				chC[idx] = a.Cvec[(size_t) v * W + w];
+	for (int base = 0; base < T;) {
+		/* ---- stage the vectors of the next rows (as many rows as fit WIN_ECAP entries) */
+		if (tid == 0) {
+			int rows = 0, ent = 0;
+			while (base + rows < T && ent + tnc[base + rows] <= WIN_ECAP) {
+				ch_off[rows] = ent;
+				ent += tnc[base + rows];
+				rows++;
 			}
+			ch_off[rows] = ent;
+			s_rows = rows;
 		}
 		__syncthreads();
+		const int rows_here = s_rows;
+		const int nent = ch_off[rows_here];
+		for (int r = tid; r < rows_here; r += blockDim.x) {
+			const int b = tl[base + r];
+			for (int k = 0; k < tnc[base + r]; k++)
+				ch_vec[ch_off[r] + k] = a.slotvec[b * WIN_MAXC + k];
+		}
+		__syncthreads();
+		for (int idx = tid; idx < nent * W; idx += blockDim.x) {
+			const int v = ch_vec[idx / W];
+			const int w = idx % W;
+			chR[idx] = a.Rvec[(size_t) v * W + w];
+			chC[idx] = a.Cvec[(size_t) v * W + w];
+		}
+		__syncthreads();
+		/* ---- the rows of the chunk, in order; everything below touches shared memory only */
 		for (int r = 0; r < rows_here; r++, iter++) {
 			const int b = tl[base + r];
 			if (warp == 0) {
 				const unsigned Ev = lane < W ? Et[lane * Wn + b] : 0u;
 				const unsigned cm = lane < W ? s_committed[lane] : 0u;
-				const int nc = a.slotnc[b];
+				const int nc = tnc[base + r], off = ch_off[r];
 				int pick = -1;
 				unsigned reff = 0, c0 = 0;
 				for (int k = 0; k < nc; k++) {
-					const int v = a.slotvec[b * WIN_MAXC + k];
+					const int v = ch_vec[off + k];
 					if (taken[v >> 5] & (1u << (v & 31)))
 						continue;                               /* became pivotal inside this window */
-					const unsigned cv = lane < W ? chC[(r * WIN_MAXC + k) * W + lane] : 0u;
-					reff = (lane < W ? chR[(r * WIN_MAXC + k) * W + lane] : 0u) | (cv & cm);
+					const unsigned cv = lane < W ? chC[(off + k) * W + lane] : 0u;
+					reff = (lane < W ? chR[(off + k) * W + lane] : 0u) | (cv & cm);
 					c0 = cv;
 					if (!__any_sync(0xffffffffu, (reff & Ev) != 0)) {
 						pick = k;
@@ -402,15 +490,15 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 			}
 			if (tid == b)
 				mypick = pick;
-			__syncthreads();
 			if (tid == 0) {
+				/* only warp 0 reads these two, and only after the next barrier or its own __syncwarp */
 				s_committed[b >> 5] |= 1u << (b & 31);
-				const int v0 = a.slotvec[b * WIN_MAXC + pick];
+				const int v0 = ch_vec[ch_off[r] + pick];
 				taken[v0 >> 5] |= 1u << (v0 & 31);
 			}
-			if (warp == 0)
-				__syncwarp();
+			__syncthreads();
 		}
+		base += rows_here;
 		__syncthreads();
 	}
 	/* publish the new pivots and their adjacency records */
@@ -419,13 +507,14 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 		const int c0 = a.slotcol[tid * WIN_MAXC + mypick];
 		a.qinv[c0] = row;
 		a.pinv[row] = c0;
+		int ent[WIN_MAXC];
+		load_row16(a.lrow, a.slotlidx[tid], ent);
 		int cnt = 0;
 		int *rec = a.padj + (size_t) c0 * K;
-		for (i64 e = a.Ap[row]; e < a.Ap[row + 1]; e++) {
-			int c = a.Aj[e];
-			if (c != c0 && cnt < K)
-				rec[cnt++] = c;
-		}
+#pragma unroll
+		for (int k = 0; k < WIN_MAXC; k++)
+			if (ent[k] >= 0 && ent[k] != c0 && cnt < K)
+				rec[cnt++] = ent[k];
 		for (; cnt < K; cnt++)
 			rec[cnt] = -1;
 		atomicAdd(a.found, 1);
@@ -512,16 +601,19 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.ptr, off_.ptr, n + 1, s);
 	tmp.ensure(bytes + 16);
 	cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, flag.ptr, off_.ptr, n + 1, s);
-	k_win_list_rows<<<cdiv(n, 256), 256, 0, s>>>(n, flag.ptr, off_.ptr, list.ptr);
-	LAUNCHED(4);
+	LAUNCHED(3);
 	a.nlist = fetch(off_.ptr + n);
 	if (a.nlist == 0)
 		return true;
+	DevBuf<int> lrow((size_t) a.nlist * WIN_MAXC);
+	k_win_list_rows<<<cdiv(n, 256), 256, 0, s>>>(n, flag.ptr, off_.ptr, A.p, A.j, list.ptr, lrow.ptr);
+	LAUNCHED(1);
 	a.list = list.ptr;
+	a.lrow = lrow.ptr;
 	a.queue_cap = m + WIN_MAXC;
-	DevBuf<int> padj((size_t) m * a.K), counters(4), slotrow((size_t) Wn), slotnc((size_t) Wn), slotcol((size_t) Wn * WIN_MAXC),
-	    slotvec((size_t) Wn * WIN_MAXC), tent((size_t) Wn), colmark((size_t) m), replist((size_t) Wn * WIN_MAXC),
-	    queues((size_t) Wn * a.queue_cap);
+	DevBuf<int> padj((size_t) m * a.K), counters(4), slotrow((size_t) Wn), slotlidx((size_t) Wn), slotnc((size_t) Wn),
+	    slotcol((size_t) Wn * WIN_MAXC), slotvec((size_t) Wn * WIN_MAXC), tent((size_t) Wn), colmark((size_t) m),
+	    replist((size_t) Wn * WIN_MAXC), queues((size_t) Wn * a.queue_cap);
 	DevBuf<unsigned> Rvec((size_t) Wn * WIN_MAXC * a.W), Cvec((size_t) Wn * WIN_MAXC * a.W);
 	counters.zero(s);
 	colmark.fill_byte(0x7f, s);
@@ -532,6 +624,7 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.nslots = counters.ptr + 1;
 	a.nrep = counters.ptr + 2;
 	a.slotrow = slotrow.ptr;
+	a.slotlidx = slotlidx.ptr;
 	a.slotnc = slotnc.ptr;
 	a.slotcol = slotcol.ptr;
 	a.slotvec = slotvec.ptr;
@@ -541,7 +634,7 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.Rvec = Rvec.ptr;
 	a.Cvec = Cvec.ptr;
 	a.queues = queues.ptr;
-	const size_t res_smem = ((size_t) a.W * Wn + 2 * (size_t) WIN_CHUNK * WIN_MAXC * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
+	const size_t res_smem = ((size_t) a.W * Wn + 2 * (size_t) WIN_ECAP * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
 	const int max_windows = (a.nlist + Wn - 1) / Wn;
 	if (a.K == 4)
 		run_windows<4>(a, bfs_smem, res_smem, max_windows);
