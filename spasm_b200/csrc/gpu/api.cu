@@ -151,6 +151,42 @@ static void exchange_pieces(std::vector<HostPiece> &pieces)
 	pieces = std::move(all);
 }
 
+/* flag[c] = -1 on pivotal columns (the selection convention of panel_to_csr) */
+__global__ void k_flag_pivotal(int m, const int *__restrict__ qinv, int *flag)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < m)
+		flag[c] = qinv[c] >= 0 ? -1 : 0;
+}
+
+/* The L coefficients of a solved batch (reference: src/spasm_schur.c:306-318): for right-hand side r and every pivotal
+ * column j whose multiplier x[j] = X[j][r] is non-zero, the triplet (row_out[r], Uqinv[j], x[j]).  The pull-form solve
+ * leaves exactly these multipliers on the pivotal columns of the panel. */
+static void append_L_from_panel(Engine &E, struct spasm_triplet *L, const int *row_out, int R)
+{
+	cudaStream_t s = ctx().stream;
+	DevBuf<int> flag((size_t) E.m);
+	k_flag_pivotal<<<cdiv(E.m, 256), 256, 0, s>>>(E.m, E.Uqinv.ptr, flag.ptr);
+	LAUNCHED(1);
+	DevBuf<i64> Lp;
+	DevBuf<int> Lj;
+	DevBuf<i32> Lx;
+	i64 nnz = 0;
+	panel_to_csr(E.panel, flag.ptr, nullptr, 0, E.Uqinv.ptr, Lp, Lj, Lx, nnz);
+	if (nnz == 0)
+		return;
+	std::vector<i64> hp((size_t) R + 1);
+	std::vector<int> hj((size_t) nnz);
+	std::vector<i32> hx((size_t) nnz);
+	Lp.download(hp.data(), hp.size(), s);
+	Lj.download(hj.data(), hj.size(), s);
+	Lx.download(hx.data(), hx.size(), s);
+	sync();
+	for (int r = 0; r < R; r++)
+		for (i64 e = hp[r]; e < hp[r + 1]; e++)
+			spasm_add_entry(L, row_out[r], hj[e], hx[e]);
+}
+
 static void store_dense(void *S, spasm_datatype datatype, const std::vector<i32> &host, int rows, int ld, int Sm)
 {
 	for (int r = 0; r < rows; r++)
@@ -172,8 +208,6 @@ int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, 
 		spasm_echelonize_init_opts(&defaults);
 		opts = &defaults;
 	}
-	if (fact->Ltmp != NULL)
-		errx(1, "[spasm-b200] spasm_pivots_extract_structural: the L path is not part of the B200 build");
 	ctx();
 	struct spasm_csr *U = fact->U;
 	Engine E;
@@ -202,6 +236,21 @@ int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, 
 		for (int k = 0; k < npiv; k++)
 			U->p[un0 + k + 1] = hp[k + 1];
 		U->n = un0 + npiv;
+		if (fact->Ltmp != NULL) {
+			/* L[row of A, new row of U] = the pivot before it was scaled to 1 (pivots.c:409-426); row p[k] of A became
+			 * row un0 + k of U, its pivot column is the first entry of that row */
+			for (int k = 0; k < npiv; k++) {
+				const int i = p[k], j = U->j[U->p[un0 + k]];
+				spasm_ZZp pivot = 0;
+				for (i64 px = A->p[i]; px < A->p[i + 1] && pivot == 0; px++)
+					if (A->j[px] == j)
+						pivot = A->x[px];
+				const int i_out = (p_in != NULL) ? p_in[i] : i;
+				spasm_add_entry(fact->Ltmp, i_out, un0 + k, pivot);
+				if (fact->p != NULL)
+					fact->p[un0 + k] = i_out;
+			}
+		}
 	}
 	E.Uqinv.download(fact->qinv, (size_t) A->m, s);
 	sync();
@@ -247,8 +296,6 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
 void spasm_schur_dense(const struct spasm_csr *A, const int *p, int n, const int *p_in,
                        struct spasm_lu *fact, void *S, spasm_datatype datatype, int *q, int *p_out)
 {
-	if (fact->Ltmp != NULL)
-		errx(1, "[spasm-b200] spasm_schur_dense: the L path is not part of the B200 build");
 	ctx();
 	Engine E;
 	engine_from_host(E, fact->U, fact->qinv);
@@ -269,6 +316,12 @@ void spasm_schur_dense(const struct spasm_csr *A, const int *p, int n, const int
 		DevBuf<int> d_rows;
 		d_rows.upload(p + done, (size_t) R, s);
 		E.solve_rows(dA, d_rows.ptr, R, false);
+		if (fact->Ltmp != NULL) {
+			std::vector<int> row_out((size_t) R);
+			for (int r = 0; r < R; r++)
+				row_out[r] = (p_in != NULL) ? p_in[p[done + r]] : p[done + r];
+			append_L_from_panel(E, fact->Ltmp, row_out.data(), R);
+		}
 		B.ensure((size_t) R * std::max(ld, 4));
 		E.gather_q0(B.ptr, ld);
 		host.resize((size_t) R * std::max(ld, 4));

@@ -142,8 +142,9 @@ void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ld
 		k_gemm_sub<false><<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
 	LAUNCHED(1);
 	KERNEL_CHECK();
-	if (!d_K)
-		stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
+	/* the rank-<=32 trailing updates of the panels (d_K: the rank is only known on the device) are counted at the panel
+	 * width, an upper bound that is exact for full-rank panels: they are dense work too, executed on CUDA cores */
+	stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
 }
 
 /* ================================================================== gathers */

@@ -1055,6 +1055,21 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			 * is the same; here it is computed block-wise on the GPU.  (a sequential GPU GPLU
 			 * is a later row.)  No low-rank switch: GPLU processes every row. */
 			st.pub.finish = 3;
+			{
+				/* the block path keeps every new pivot row as a dense row over the columns that are non-pivotal now:
+				 * rank_ub x Sm x 4 bytes (+ the packed copy).  The reference keeps U sparse here.  Refuse early, with
+				 * the numbers, instead of failing inside an allocation half way through. */
+				const double Sm_now = (double) (m - E.U.n);
+				const double rank_ub = (double) std::min(n - npiv, m - E.U.n);
+				const double need = rank_ub * Sm_now * 5.0;
+				size_t free_b = 0, total_b = 0;
+				CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+				if (need > 0.8 * (double) total_b)
+					errx(1, "[spasm-b200] the sparse (GPLU) finisher is executed block-wise with dense pivot rows: %.0f x %.0f remaining "
+					        "rows x columns need about %.1f GB of HBM (%.1f GB on this device). Pre-process the matrix (tools/vertical_swap, "
+					        "--dense-threshold) so that fewer columns remain, or raise --max-iterations", rank_ub, Sm_now, need / 1e9,
+					     (double) total_b / 1e9);
+			}
 			struct echelonize_opts o2 = *opts;
 			o2.enable_tall_and_skinny = 0;
 			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2, &spec);

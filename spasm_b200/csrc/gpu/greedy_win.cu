@@ -38,6 +38,7 @@ namespace sb {
 #define WIN_MAXC 16
 #define WIN_ECAP 256           /* candidate entries whose vectors are staged in shared memory at a time (phase B) */
 #define WIN_BFS_THREADS 256
+#define WIN_BFS_PER 4            /* frontier entries per thread and slice (phase A) */
 #define WIN_RING 4096          /* frontier ring in shared memory (phase A); the global queue holds everything */
 
 struct WinArgs {
@@ -298,21 +299,40 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 		 * thread takes the same decisions */
 		if (head >= tail || alive <= 0)
 			break;
-		const int cnt = min(WIN_BFS_THREADS, tail - head);
+		const int cnt = min(WIN_BFS_PER * WIN_BFS_THREADS, tail - head);
 		const bool in_ring = tail - head <= WIN_RING;
-		if (tid < cnt) {
-			const int j = in_ring ? ring[(head + tid) & (WIN_RING - 1)] : queue[head + tid];
-			int adj[K];
+		/* up to WIN_BFS_PER frontier entries per thread: their adjacency records are loaded together (a slice costs one
+		 * L2 round trip whatever its width).  The entries are taken out of the ring before anybody pushes: the pushes
+		 * of a wide slice may wrap around it. */
+		int js[WIN_BFS_PER];
 #pragma unroll
-			for (int k = 0; k < K; k += 4) {
-				const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) j * K + k);
-				adj[k] = v.x; adj[k + 1] = v.y; adj[k + 2] = v.z; adj[k + 3] = v.w;
+		for (int u = 0; u < WIN_BFS_PER; u++) {
+			const int q = head + tid + u * WIN_BFS_THREADS;
+			js[u] = (q < head + cnt) ? (in_ring ? ring[q & (WIN_RING - 1)] : queue[q]) : -1;
+		}
+		__syncthreads();
+		if (js[0] >= 0) {
+			int adj[WIN_BFS_PER][K];
+#pragma unroll
+			for (int u = 0; u < WIN_BFS_PER; u++) {
+				if (js[u] >= 0) {
+#pragma unroll
+					for (int k = 0; k < K; k += 4) {
+						const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) js[u] * K + k);
+						adj[u][k] = v.x; adj[u][k + 1] = v.y; adj[u][k + 2] = v.z; adj[u][k + 3] = v.w;
+					}
+				} else {
+					adj[u][0] = -2;
+				}
 			}
-			if (adj[0] != -2) {
+#pragma unroll
+			for (int u = 0; u < WIN_BFS_PER; u++) {
+				if (adj[u][0] == -2)
+					continue;
 				my_edges += 1;
 #pragma unroll
 				for (int k = 0; k < K; k++) {
-					const int c = adj[k];
+					const int c = adj[u][k];
 					if (c < 0)
 						continue;
 					my_edges += 1;
@@ -325,16 +345,16 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 					}
 				}
 			}
-		} else if (cnt <= WIN_BFS_THREADS - 32 && tid >= WIN_BFS_THREADS - 32) {
-			/* the last warp is rarely busy with the frontier: it recounts the survivors (marks of the earlier slices) */
+		}
+		if (tid >= WIN_BFS_THREADS - 32) {
+			/* the last warp recounts the survivors (marks of the earlier slices and part of this one) */
+			__syncwarp();
 			const int l = tid - (WIN_BFS_THREADS - 32);
 			const bool live = l < s_nc && !(vis[s_cand[l] >> 5] & (1u << (s_cand[l] & 31)));
 			const unsigned mask = __ballot_sync(0xffffffffu, live);
 			if (l == 0)
 				s_alive[(iter + 1) & 1] = __popc(mask);
 		}
-		if (cnt > WIN_BFS_THREADS - 32 && tid == 0)
-			s_alive[(iter + 1) & 1] = alive;      /* full slice: carry the count over, recount later */
 		head += cnt;
 		__syncthreads();
 		tail = s_tail;
@@ -368,13 +388,14 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 	}
 }
 
-/* ------------------------------------------------------------------ phase B: ordered resolution, one CTA, blockDim == Wn */
+/* ------------------------------------------------------------------ phase B: ordered resolution, one CTA, blockDim == Wn = 32 W */
 
-template <int K>
-__global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
+template <int K, int W>
+__global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 {
+	constexpr int Wn = 32 * W;
+	constexpr int NWARPS = W;
 	extern __shared__ unsigned dyn[];
-	const int Wn = a.Wn, W = a.W;
 	unsigned *Et = dyn;                                            /* Et[w * Wn + t]: word w of E[t] */
 	unsigned *chR = Et + (size_t) W * Wn;                          /* WIN_ECAP * W */
 	unsigned *chC = chR + (size_t) WIN_ECAP * W;
@@ -384,8 +405,10 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 	__shared__ int ch_vec[WIN_ECAP];
 	__shared__ int ch_off[WIN_ECAP + 1];
 	__shared__ int s_warpcnt[32];
-	__shared__ unsigned s_committed[32], s_reff[32], s_c0[32];
-	__shared__ int s_pick[2], s_T, s_rows;
+	__shared__ unsigned s_committed[32];
+	__shared__ unsigned s_reff[2][WIN_MAXC][W], s_c0[2][WIN_MAXC][W];   /* per candidate of the current row (double-buffered) */
+	__shared__ unsigned s_hit[3];                                  /* bit k: candidate k is reached (or no candidate any more); rotated */
+	__shared__ int s_T, s_rows;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nslots = *a.nslots;
 	if (nslots == 0)
@@ -394,14 +417,16 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 	const unsigned bal = __ballot_sync(0xffffffffu, tentative);
 	if (lane == 0)
 		s_warpcnt[warp] = __popc(bal);
-	for (int idx = tid; idx < W * Wn; idx += blockDim.x) {
+	for (int idx = tid; idx < W * Wn; idx += Wn) {
 		const int w = idx / Wn, t = idx - w * Wn;
 		Et[idx] = (w == (t >> 5)) ? (1u << (t & 31)) : 0u;
 	}
-	for (int idx = tid; idx < (Wn * WIN_MAXC) / 32; idx += blockDim.x)
+	for (int idx = tid; idx < (Wn * WIN_MAXC) / 32; idx += Wn)
 		taken[idx] = 0;
 	if (tid < 32)
 		s_committed[tid] = 0;
+	if (tid < 3)
+		s_hit[tid] = 0;
 	__syncthreads();
 	{
 		int before = 0;
@@ -412,13 +437,13 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 			tl[t] = tid;
 			tnc[t] = (unsigned char) a.slotnc[tid];
 		}
-		if (tid == blockDim.x - 1)
+		if (tid == Wn - 1)
 			s_T = before + __popc(bal);
 	}
 	__syncthreads();
 	const int T = s_T;
 	int mypick = -1;
-	int iter = 0;                       /* s_pick is double-buffered: a slow warp may still have to read the previous decision */
+	int iter = 0;                       /* the per-row scratch is double-buffered: a slow warp may still read the previous row's */
 	for (int base = 0; base < T;) {
 		/* ---- stage the vectors of the next rows (as many rows as fit WIN_ECAP entries) */
 		if (tid == 0) {
@@ -434,13 +459,13 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 		__syncthreads();
 		const int rows_here = s_rows;
 		const int nent = ch_off[rows_here];
-		for (int r = tid; r < rows_here; r += blockDim.x) {
+		for (int r = tid; r < rows_here; r += Wn) {
 			const int b = tl[base + r];
 			for (int k = 0; k < tnc[base + r]; k++)
 				ch_vec[ch_off[r] + k] = a.slotvec[b * WIN_MAXC + k];
 		}
 		__syncthreads();
-		for (int idx = tid; idx < nent * W; idx += blockDim.x) {
+		for (int idx = tid; idx < nent * W; idx += Wn) {
 			const int v = ch_vec[idx / W];
 			const int w = idx % W;
 			chR[idx] = a.Rvec[(size_t) v * W + w];
@@ -450,50 +475,51 @@ __global__ void __launch_bounds__(1024) k_win_resolve(WinArgs a)
 		/* ---- the rows of the chunk, in order; everything below touches shared memory only */
 		for (int r = 0; r < rows_here; r++, iter++) {
 			const int b = tl[base + r];
-			if (warp == 0) {
-				const unsigned Ev = lane < W ? Et[lane * Wn + b] : 0u;
-				const unsigned cm = lane < W ? s_committed[lane] : 0u;
-				const int nc = tnc[base + r], off = ch_off[r];
-				int pick = -1;
-				unsigned reff = 0, c0 = 0;
-				for (int k = 0; k < nc; k++) {
-					const int v = ch_vec[off + k];
-					if (taken[v >> 5] & (1u << (v & 31)))
-						continue;                               /* became pivotal inside this window */
-					const unsigned cv = lane < W ? chC[(off + k) * W + lane] : 0u;
-					reff = (lane < W ? chR[(off + k) * W + lane] : 0u) | (cv & cm);
-					c0 = cv;
-					if (!__any_sync(0xffffffffu, (reff & Ev) != 0)) {
-						pick = k;
-						break;
-					}
+			const int nc = tnc[base + r], off = ch_off[r];
+			const int pb = iter & 1, hb = iter % 3;
+			/* the hit mask of the NEXT row is cleared here: its previous use (two rows ago) was read before the
+			 * barrier of the previous row, and its next writers come after the barrier below */
+			if (tid == 0)
+				s_hit[(iter + 1) % 3] = 0;
+			/* one warp per candidate entry: is it reached by row b or by a search row b inherits? */
+			for (int k = warp; k < nc; k += NWARPS) {
+				const int v = ch_vec[off + k];
+				const bool gone = (taken[v >> 5] >> (v & 31)) & 1u;              /* became pivotal inside this window */
+				unsigned reff = 0, cv = 0, Ev = 0;
+				if (lane < W) {
+					cv = chC[(off + k) * W + lane];
+					reff = chR[(off + k) * W + lane] | (cv & s_committed[lane]);
+					Ev = Et[lane * Wn + b];
+					s_reff[pb][k][lane] = reff;
+					s_c0[pb][k][lane] = cv;
 				}
-				if (pick >= 0 && lane < W) {
-					s_reff[lane] = reff;
-					s_c0[lane] = c0;
-				}
-				if (lane == 0)
-					s_pick[iter & 1] = pick;
+				const bool hit = __any_sync(0xffffffffu, (reff & Ev) != 0) || gone;
+				if (lane == 0 && hit)
+					atomicOr(&s_hit[hb], 1u << k);
 			}
 			__syncthreads();
-			const int pick = s_pick[iter & 1];
-			if (pick < 0)
-				continue;                                       /* uniform: every thread read the same value */
+			const unsigned hitmask = s_hit[hb];
+			const unsigned freemask = ~hitmask & ((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1));
+			if (freemask == 0)
+				continue;                                       /* uniform: no survivor, row b fails */
+			const int pick = __ffs(freemask) - 1;               /* first survivor in row order (pivots.c:233-237) */
 			/* commit (b, pick): the later rows that reach the new pivot inherit the search of row b */
 			if (tentative && tid > b) {
-				bool hit = (s_c0[tid >> 5] >> (tid & 31)) & 1u;
-				for (int w = 0; w < W && !hit; w++)
-					hit = (Et[w * Wn + tid] & s_reff[w]) != 0;
-				if (hit)
+				bool hit = (s_c0[pb][pick][tid >> 5] >> (tid & 31)) & 1u;
+#pragma unroll
+				for (int w = 0; w < W; w++)
+					hit |= (Et[w * Wn + tid] & s_reff[pb][pick][w]) != 0;
+				if (hit) {
+#pragma unroll
 					for (int w = 0; w < W; w++)
 						Et[w * Wn + tid] |= Et[w * Wn + b];
+				}
 			}
 			if (tid == b)
 				mypick = pick;
 			if (tid == 0) {
-				/* only warp 0 reads these two, and only after the next barrier or its own __syncwarp */
 				s_committed[b >> 5] |= 1u << (b & 31);
-				const int v0 = ch_vec[ch_off[r] + pick];
+				const int v0 = ch_vec[off + pick];
 				taken[v0 >> 5] |= 1u << (v0 & 31);
 			}
 			__syncthreads();
@@ -540,12 +566,12 @@ __global__ void k_win_cleanup(WinArgs a)
 
 /* ------------------------------------------------------------------ driver */
 
-template <int K>
+template <int K, int W>
 static void run_windows(WinArgs &a, size_t bfs_smem, size_t res_smem, int max_windows)
 {
 	cudaStream_t s = ctx().stream;
 	CUDA_CHECK(cudaFuncSetAttribute(k_win_bfs<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bfs_smem));
-	CUDA_CHECK(cudaFuncSetAttribute(k_win_resolve<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) res_smem));
+	CUDA_CHECK(cudaFuncSetAttribute(k_win_resolve<K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) res_smem));
 	k_win_padj_init<K><<<cdiv(a.m, 256), 256, 0, s>>>(a.m, a.Ap, a.Aj, a.qinv, a.padj);
 	LAUNCHED(1);
 	int done = 0;
@@ -554,7 +580,7 @@ static void run_windows(WinArgs &a, size_t bfs_smem, size_t res_smem, int max_wi
 		for (int w = 0; w < batch; w++) {
 			k_win_form<<<1, 1024, 0, s>>>(a);
 			k_win_bfs<K><<<a.Wn, WIN_BFS_THREADS, bfs_smem, s>>>(a);
-			k_win_resolve<K><<<1, a.Wn, res_smem, s>>>(a);
+			k_win_resolve<K, W><<<1, a.Wn, res_smem, s>>>(a);
 			k_win_cleanup<<<cdiv((size_t) a.Wn * WIN_MAXC, 256), 256, 0, s>>>(a);
 		}
 		LAUNCHED(4 * batch);
@@ -582,7 +608,7 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	if (bfs_smem > 160 * 1024)
 		return false;
 	int Wn = getenv("SPASM_B200_GREEDY_WINDOW") ? atoi(getenv("SPASM_B200_GREEDY_WINDOW")) : 512;
-	Wn = std::max(64, std::min(1024, (Wn + 31) / 32 * 32));
+	Wn = Wn >= 1024 ? 1024 : (Wn >= 512 ? 512 : 256);
 	a.Wn = Wn;
 	a.W = Wn / 32;
 	a.K = longest_row <= 5 ? 4 : (longest_row <= 9 ? 8 : 16);
@@ -636,12 +662,21 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.queues = queues.ptr;
 	const size_t res_smem = ((size_t) a.W * Wn + 2 * (size_t) WIN_ECAP * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
 	const int max_windows = (a.nlist + Wn - 1) / Wn;
+#define WIN_DISPATCH(KK)                                                   \
+	do {                                                                   \
+		if (a.W == 8)                                                      \
+			run_windows<KK, 8>(a, bfs_smem, res_smem, max_windows);        \
+		else if (a.W == 16)                                                \
+			run_windows<KK, 16>(a, bfs_smem, res_smem, max_windows);       \
+		else                                                               \
+			run_windows<KK, 32>(a, bfs_smem, res_smem, max_windows);       \
+	} while (0)
 	if (a.K == 4)
-		run_windows<4>(a, bfs_smem, res_smem, max_windows);
+		WIN_DISPATCH(4);
 	else if (a.K == 8)
-		run_windows<8>(a, bfs_smem, res_smem, max_windows);
+		WIN_DISPATCH(8);
 	else
-		run_windows<16>(a, bfs_smem, res_smem, max_windows);
+		WIN_DISPATCH(16);
 	return true;
 }
 

@@ -200,15 +200,23 @@ __global__ void k_kahn_async(int n, const i64 *__restrict__ rptr, const int *__r
 		if (s < 0) {
 			if (lane == 0) {
 				const int t = atomicAdd(ticket, 1);
+				/* watchdog on PROGRESS, not on elapsed spins: the budget restarts whenever another node completes, so a
+				 * long valid pass is never mistaken for a cycle; only "nothing completes any more" raises the flag */
+				int seen_done = -1;
 				for (long spin = 0;; spin++) {
 					if (t < n) {
 						s = *((volatile int *) &order[t]);
 						if (s >= 0)
 							break;
 					}
-					if (*((volatile int *) done) >= n || *((volatile int *) error)) {
+					const int d_now = *((volatile int *) done);
+					if (d_now >= n || *((volatile int *) error)) {
 						s = -2;
 						break;
+					}
+					if (d_now != seen_done) {
+						seen_done = d_now;
+						spin = 0;
 					}
 					if (spin > (1L << 24)) {
 						*error = 1;
@@ -587,15 +595,21 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 			if (tid == 0) {
 				const int t = atomicAdd(ticket, 1);
 				int got = -2;
+				int seen_done = -1;      /* progress-based watchdog: the budget restarts whenever a column completes */
 				for (long spin = 0;; spin++) {
 					if (t < nscheduled) {
 						got = *((volatile int *) &queue[t]);
 						if (got >= 0)
 							break;
 					}
-					if (*((volatile int *) done) >= nscheduled || *((volatile int *) error)) {
+					const int d_now = *((volatile int *) done);
+					if (d_now >= nscheduled || *((volatile int *) error)) {
 						got = -2;
 						break;
+					}
+					if (d_now != seen_done) {
+						seen_done = d_now;
+						spin = 0;
 					}
 					if (spin > (1L << 24)) {
 						*error = 1;
@@ -740,6 +754,284 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
 	}
 }
 
+/*
+ * Dataflow solve, second version: the hop of a chain without a global-memory round trip on its critical path.
+ *
+ * In k_panel_solve_flow a CTA that walks a chain c -> d pays, per hop: store X[c], __threadfence, atomicSub on the
+ * pending counter of d (an L2 round trip), then the reload of X[c] it has just written.  Here:
+ *   - REGISTER FORWARDING: thread r keeps X[c][r] in a register; the next column reads its dependency on c from there.
+ *   - CERTAIN CONTINUATION: every column gets a `doneflag`, set by its CTA AFTER it has decremented the counters of all
+ *     its dependents.  While c is being computed, a prefetch warp loads the dependency lists of c's dependents and
+ *     checks the flags of their OTHER dependencies: if they are all set, every other decrement of pending[d] has
+ *     happened, c's own would be the last one, so this CTA owns d -- it goes on with d at once, without the atomic.
+ *   - DEFERRED PUBLICATION: the fence, the decrements of the other dependents, the flag and the `done` count of c are
+ *     issued by a publisher warp during the computation of d (two service warps per CTA; the metadata buffers are
+ *     double-buffered so the prefetch of d's dependents does not overwrite what the publication of c still reads).
+ * When no dependent is certain the CTA publishes at once and continues with a dependent its decrements released
+ * (as before), or polls the queue.  Each column is still written once, from final columns: same values.
+ * Needs one right-hand-side group per compute thread (R4 <= blockDim.x - 64); wider batches take the first version.
+ */
+struct FlowMeta2 {
+	int node, cnt, ready, pad;
+	i64 e0, rb, re;
+	int src[FLOW_MAXE];
+	i32 val[FLOW_MAXE];
+};
+
+struct FlowPub {
+	int valid, node, buf, skip;
+	i64 rb, re;
+};
+
+__device__ __forceinline__ void flow2_publish(const FlowPub &pb, const FlowMeta2 *depbuf, const int *__restrict__ rdst, int *pending,
+                                              int *queue, int *tail, int *done, int *doneflag, int *s_next, bool capture, int lane)
+{
+	__threadfence();                 /* the column was stored by the compute threads before the CTA barrier that precedes this */
+	for (i64 k = pb.rb + lane; k < pb.re; k += 32) {
+		const int di = (int) (k - pb.rb);
+		if (di == pb.skip)
+			continue;                /* the dependent this CTA went on with: its counter is left alone */
+		const int d = (di < FLOW_MAXD) ? depbuf[di].node : rdst[k];
+		if (atomicSub(&pending[d], 1) == 1) {
+			if (!(capture && di < FLOW_MAXD && atomicCAS(s_next, -1, di) == -1)) {
+				const int pos = atomicAdd(tail, 1);
+				__threadfence();
+				*((volatile int *) &queue[pos]) = d;
+			}
+		}
+	}
+	__syncwarp();
+	__threadfence();                 /* the decrements before the flag: a set flag means "my decrements are done" */
+	if (lane == 0) {
+		*((volatile int *) &doneflag[pb.node]) = 1;
+		atomicAdd(done, 1);
+	}
+}
+
+__global__ void __launch_bounds__(1024)
+k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+                    const i64 *__restrict__ rptr, const int *__restrict__ rdst,
+                    int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
+                    int4 *X, int ld4, int R4, Zp F, int *level_out)
+{
+	__shared__ int s_node, s_next;
+	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
+	__shared__ FlowPub pub;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int T3 = blockDim.x - 64;                       /* compute threads */
+	const bool is_prefetch = tid >= T3 && tid < T3 + 32;
+	const bool is_publish = tid >= T3 + 32;
+	int buf = 0;
+	bool have_cur = false;
+	int fwd_col = -1;
+	int4 fwd = make_int4(0, 0, 0, 0);
+	if (tid == 0)
+		pub.valid = 0;
+	__syncthreads();
+	for (;;) {
+		/* ---- 1. the job */
+		if (!have_cur) {
+			if (tid == 0) {
+				const int t = atomicAdd(ticket, 1);
+				int got = -2;
+				int seen_done = -1;      /* progress-based watchdog */
+				for (long spin = 0;; spin++) {
+					if (t < nscheduled) {
+						got = *((volatile int *) &queue[t]);
+						if (got >= 0)
+							break;
+					}
+					const int d_now = *((volatile int *) done);
+					if (d_now >= nscheduled || *((volatile int *) error)) {
+						got = -2;
+						break;
+					}
+					if (d_now != seen_done) {
+						seen_done = d_now;
+						spin = 0;
+					}
+					if (spin > (1L << 24)) {
+						*error = 1;
+						got = -2;
+						break;
+					}
+					__nanosleep(100);
+				}
+				__threadfence();
+				s_node = got;
+			}
+			__syncthreads();
+			const int c0 = s_node;
+			if (c0 < 0)
+				return;
+			const i64 e0 = ptr[c0];
+			const int cnt = (int) (ptr[c0 + 1] - e0);
+			if (tid < FLOW_MAXE && tid < cnt) {
+				cur.src[tid] = src[e0 + tid];
+				cur.val[tid] = val[e0 + tid];
+			}
+			if (tid == 0) {
+				cur.node = c0;
+				cur.cnt = cnt;
+				cur.e0 = e0;
+				cur.rb = rptr[c0];
+				cur.re = rptr[c0 + 1];
+			}
+			fwd_col = -1;
+		}
+		__syncthreads();                                  /* [A] cur is ready */
+		const int c = cur.node;
+		const i64 rb = cur.rb, re = cur.re;
+		if (tid < T3) {
+			/* ---- 2a. the column, one group of four right-hand sides per thread */
+			if (tid < R4) {
+				const int r = tid;
+				const int cnt = cur.cnt, cached = min(cnt, FLOW_MAXE);
+				const i64 e0 = cur.e0;
+				int4 *Xc = X + (size_t) c * ld4;
+				int4 b = Xc[r];
+				i64 a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+				int pendingred = 0;
+				int e = 0;
+				for (; F.delay >= 4 && e + 4 <= cnt; e += 4) {
+					i64 v[4];
+					int4 xs[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const int sc = (e + u < cached) ? cur.src[e + u] : src[e0 + e + u];
+						v[u] = (e + u < cached) ? cur.val[e + u] : val[e0 + e + u];
+						xs[u] = (sc == fwd_col) ? fwd : __ldcg(&X[(size_t) sc * ld4 + r]);
+					}
+					if (pendingred + 4 > F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pendingred = 0;
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						a0 -= v[u] * xs[u].x;
+						a1 -= v[u] * xs[u].y;
+						a2 -= v[u] * xs[u].z;
+						a3 -= v[u] * xs[u].w;
+					}
+					pendingred += 4;
+				}
+				for (; e < cnt; e++) {
+					const i64 v = (e < cached) ? cur.val[e] : val[e0 + e];
+					const int sc = (e < cached) ? cur.src[e] : src[e0 + e];
+					const int4 xs = (sc == fwd_col) ? fwd : __ldcg(&X[(size_t) sc * ld4 + r]);
+					if (pendingred + 1 > F.delay) {
+						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
+						pendingred = 0;
+					}
+					a0 -= v * xs.x;
+					a1 -= v * xs.y;
+					a2 -= v * xs.z;
+					a3 -= v * xs.w;
+					pendingred++;
+				}
+				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
+				Xc[r] = b;
+				fwd = b;
+			}
+			fwd_col = c;
+			/* lazy schedule: the level of the column is a by-product of the pass (its dependencies are final) */
+			if (level_out && tid == T3 - 1) {
+				const int cnt = cur.cnt;
+				const i64 e0 = cur.e0;
+				int lv = 0;
+				for (int e = 0; e < cnt; e++)
+					lv = max(lv, __ldcg(&level_out[(e < FLOW_MAXE) ? cur.src[e] : src[e0 + e]]));
+				level_out[c] = lv + 1;
+			}
+		} else if (is_prefetch) {
+			/* ---- 2b. metadata of the dependents of c, and whether c is the last dependency they wait for */
+			FlowMeta2 *dp = dep[buf];
+			for (int pass = 0; pass < (FLOW_MAXD * FLOW_MAXE) / 32; pass++) {
+				const int item = pass * 32 + lane;
+				const int di = item / FLOW_MAXE, ei = item % FLOW_MAXE;
+				bool ok = true;                       /* this dependency does not stand in the way */
+				int dcnt = 0;
+				if (rb + di < re) {
+					const int d = rdst[rb + di];
+					const i64 de0 = ptr[d];
+					dcnt = (int) (ptr[d + 1] - de0);
+					if (ei < dcnt) {
+						const int sc = src[de0 + ei];
+						dp[di].src[ei] = sc;
+						dp[di].val[ei] = val[de0 + ei];
+						ok = (sc == c) || (*((volatile int *) &doneflag[sc]) != 0);
+					}
+					if (ei == 0) {
+						dp[di].node = d;
+						dp[di].cnt = dcnt;
+						dp[di].e0 = de0;
+						dp[di].rb = rptr[d];
+						dp[di].re = rptr[d + 1];
+					}
+				} else {
+					ok = false;
+				}
+				const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+				if (ei == 0) {
+					const unsigned mine = (okmask >> (lane & ~(FLOW_MAXE - 1))) & ((1u << FLOW_MAXE) - 1);
+					dp[di].ready = (rb + di < re) && dcnt <= FLOW_MAXE && mine == ((1u << FLOW_MAXE) - 1);
+				}
+			}
+			__threadfence();                          /* flags read before the panel vectors of those columns are */
+		} else if (is_publish) {
+			/* ---- 2c. publication of the previous column of the chain (deferred by one hop) */
+			if (pub.valid)
+				flow2_publish(pub, dep[pub.buf], rdst, pending, queue, tail, done, doneflag, &s_next, false, lane);
+		}
+		__syncthreads();                                  /* [B] */
+		/* ---- 3. go on with a dependent that is certain to be released by c, if there is one */
+		if (tid == 0) {
+			int pick = -1;
+			const int nd = (int) min((i64) FLOW_MAXD, re - rb);
+			for (int di = 0; di < nd && pick < 0; di++)
+				if (dep[buf][di].ready)
+					pick = di;
+			s_next = pick;
+			pub.valid = pick >= 0;
+			pub.node = c;
+			pub.buf = buf;
+			pub.skip = pick;
+			pub.rb = rb;
+			pub.re = re;
+		}
+		__syncthreads();                                  /* [C] */
+		int nxt = s_next;
+		if (nxt < 0) {
+			/* nobody is certain: publish now, keep a dependent the decrements release (if any) */
+			if (is_publish) {
+				FlowPub now;
+				now.valid = 1; now.node = c; now.buf = buf; now.skip = -1; now.rb = rb; now.re = re;
+				flow2_publish(now, dep[buf], rdst, pending, queue, tail, done, doneflag, &s_next, true, lane);
+			}
+			__syncthreads();
+			nxt = s_next;
+		}
+		if (nxt >= 0) {
+			const FlowMeta2 *nx = &dep[buf][nxt];
+			if (tid < FLOW_MAXE) {
+				cur.src[tid] = nx->src[tid];
+				cur.val[tid] = nx->val[tid];
+			}
+			if (tid == 0) {
+				cur.node = nx->node;
+				cur.cnt = nx->cnt;
+				cur.e0 = nx->e0;
+				cur.rb = nx->rb;
+				cur.re = nx->re;
+			}
+			have_cur = true;
+		} else {
+			have_cur = false;
+		}
+		buf ^= 1;
+	}
+}
+
 /* Dataflow solve of a very sparse batch (spasm_rref: a row of the RREF touches a fraction of a percent of the
  * columns).  Same schedule as k_panel_solve_flow; per column the CTA first ORs the occupancy masks of the column and
  * of its dependencies (mw words: 128 right-hand sides per word), lists the marked groups in shared memory and computes
@@ -759,15 +1051,21 @@ k_panel_solve_flow_masked(const i64 *__restrict__ ptr, const int *__restrict__ s
 			if (got < 0) {
 				const int t = atomicAdd(ticket, 1);
 				got = -2;
+				int seen_done = -1;      /* progress-based watchdog: the budget restarts whenever a column completes */
 				for (long spin = 0;; spin++) {
 					if (t < nscheduled) {
 						got = *((volatile int *) &queue[t]);
 						if (got >= 0)
 							break;
 					}
-					if (*((volatile int *) done) >= nscheduled || *((volatile int *) error)) {
+					const int d_now = *((volatile int *) done);
+					if (d_now >= nscheduled || *((volatile int *) error)) {
 						got = -2;
 						break;
+					}
+					if (d_now != seen_done) {
+						seen_done = d_now;
+						spin = 0;
 					}
 					if (spin > (1L << 24)) {
 						*error = 1;
@@ -888,6 +1186,14 @@ void panel_solve_masked(const DepGraph &G, i32 *X, int ld, int R, unsigned *mask
 	st.pub.solve_rows += R;
 }
 
+/* columns without dependency are final from the start */
+__global__ void k_flow2_flags(int n, const i64 *__restrict__ ptr, int *doneflag)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < n)
+		doneflag[c] = (ptr[c + 1] == ptr[c]);
+}
+
 void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 {
 	if (G.nlevels <= 1 || R <= 0)
@@ -908,10 +1214,27 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		/* one pass over the right-hand sides per column when possible: the column is the unit of the critical path */
 		int threads = getenv("SPASM_B200_FLOW_THREADS") ? atoi(getenv("SPASM_B200_FLOW_THREADS")) : (R4 > 480 ? 1024 : R4 > 224 ? 512 : 256);      /* one warp of the CTA is the prefetcher when the batch fits */
 		threads = std::max(64, std::min(1024, threads & ~31));
+		static const bool flow1 = getenv("SPASM_B200_FLOW1") != NULL;
+		const bool flow2 = !flow1 && R4 <= 1024 - 64;      /* one right-hand-side group per compute thread: register forwarding */
+		GpuTimer tk;
+		if (flow2) {
+			threads = R4 + 64 > 512 ? 1024 : R4 + 64 > 256 ? 512 : 256;
+			DevBuf<int> doneflag((size_t) n);
+			k_flow2_flags<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr.ptr, doneflag.ptr);
+			int occ = 0;
+			CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow2, threads, 0));
+			int blocks = std::max(1, std::min(occ, 8)) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
+			tk.start();
+			k_panel_solve_flow2<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
+			                                          G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3, doneflag.ptr,
+			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr);
+			LAUNCHED(2);
+			KERNEL_CHECK();
+			stats().pub.ms_k_panel_solve += tk.stop_ms();      /* before doneflag goes out of scope: the stop synchronises */
+		} else {
 		int occ = 0;
 		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, threads, 0));
 		int blocks = std::max(1, std::min(occ, 8)) * ctx().sm_count;      /* co-resident: idle CTAs poll the queue */
-		GpuTimer tk;
 		tk.start();
 		k_panel_solve_flow<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, G.level.ptr, pending.ptr, queue.ptr,
 		                                         G.nseeds, G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3,
@@ -919,6 +1242,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		LAUNCHED(1);
 		KERNEL_CHECK();
 		stats().pub.ms_k_panel_solve += tk.stop_ms();
+		}
 		int h[4];
 		CUDA_CHECK(cudaMemcpyAsync(h, counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
 		sync();

@@ -101,11 +101,18 @@ def test_upper_triangular_solves(prog):
 @pytest.mark.parametrize("prog", ["echelonize", "kernel", "schur", "schur_dense", "dense_rref_ffpack", "sparse_utsolve"])
 def test_reference_program_on_every_fixture_and_modulus(prog):
     """tests/CMakeLists.txt spasm_run_tests_mod: 32 fixtures x 6 moduli"""
-    failures = []
-    for name in fixture_names():
-        sms = sms_of(name)
-        for p in MODULI:
-            r = run(prog, "--modulus", str(p), stdin=sms, timeout=300)
-            if r.returncode != 0 or b"not ok" in r.stdout:
-                failures.append((name, p, r.returncode, r.stdout[-200:], r.stderr[-300:]))
+    import concurrent.futures
+    jobs = [(name, p) for name in fixture_names() for p in MODULI]
+    inputs = {name: sms_of(name) for name in fixture_names()}
+
+    def one(job):
+        name, p = job
+        r = run(prog, "--modulus", str(p), stdin=inputs[name], timeout=300)
+        if r.returncode != 0 or b"not ok" in r.stdout:
+            return (name, p, r.returncode, r.stdout[-200:], r.stderr[-300:])
+        return None
+
+    # every run is its own process with its own CUDA context (~1 s of start-up each): eight at a time share the GPU
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        failures = [f for f in ex.map(one, jobs) if f is not None]
     assert not failures, f"{len(failures)} failing runs, first: {failures[:3]}"
