@@ -54,6 +54,11 @@ void spasm_b200_reset_stats(void);
 void spasm_b200_get_stats(struct spasm_b200_stats *out);
 const char *spasm_b200_version(void);
 void spasm_b200_set_verbose(int verbose);    /* 0 silences the stderr progress lines */
+/* The library allocates from a memory pool of its own (never from the device's default pool) and keeps freed blocks
+ * for the next call (blocks of 32 MB and more in a cache of up to SPASM_B200_CACHE_GB = 48 GB).  spasm_b200_trim()
+ * returns all idle device memory to the driver; call it between echelonizations when another library of the process
+ * needs the HBM.  All entry points of the library are single-threaded: call them from one thread at a time. */
+void spasm_b200_trim(void);
 
 /* Device-resident operation, for measuring the kernels without PCIe traffic: upload once, echelonize many times.
  * The echelon form of the resident variant stays on the device and is discarded; the rank is returned and

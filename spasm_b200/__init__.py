@@ -27,6 +27,7 @@ EXTRA_PROTOTYPES = {
     "spasm_b200_get_stats": (None, [C.c_void_p]),
     "spasm_b200_version": (C.c_char_p, []),
     "spasm_b200_set_verbose": (None, [C.c_int]),
+    "spasm_b200_trim": (None, []),
     "spasm_b200_upload_csr": (C.c_void_p, [abi.CsrP]),
     "spasm_b200_free_csr": (None, [C.c_void_p]),
     "spasm_b200_echelonize_resident": (C.c_int, [C.c_void_p, abi.OptsP, C.POINTER(C.c_double)]),

@@ -14,19 +14,14 @@ static Context g_ctx;
 static Stats g_stats;
 static int g_requested_device = -1;
 static bool g_verbose = true;
+static cudaMemPool_t g_pool = nullptr;
 
 Stats &stats() { return g_stats; }
 
-Context &ctx()
+static std::thread *g_warm = nullptr;      /* context creation started ahead of the first GPU call (spasm_b200_warmup_async) */
+
+static int pick_device(int count)
 {
-	if (g_ctx.device >= 0)
-		return g_ctx;
-	int count = 0;
-	cudaError_t e = cudaGetDeviceCount(&count);
-	if (e != cudaSuccess || count == 0)
-		errx(1, "[spasm-b200] no usable CUDA device (%s). This library has no CPU fallback: "
-		        "spasm_echelonize / spasm_rref / spasm_kernel / spasm_schur* run on a B200 (sm_100a) only.",
-		     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 	int dev = g_requested_device;
 	if (dev < 0) {
 		const char *s = getenv("SPASM_B200_DEVICE");
@@ -34,6 +29,25 @@ Context &ctx()
 			s = getenv("LOCAL_RANK");
 		dev = s ? atoi(s) % count : 0;
 	}
+	return dev;
+}
+
+Context &ctx()
+{
+	if (g_ctx.device >= 0)
+		return g_ctx;
+	if (g_warm) {                      /* the helper thread is creating (or has created) the primary context */
+		g_warm->join();
+		delete g_warm;
+		g_warm = nullptr;
+	}
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		errx(1, "[spasm-b200] no usable CUDA device (%s). This library has no CPU fallback: "
+		        "spasm_echelonize / spasm_rref / spasm_kernel / spasm_schur* run on a B200 (sm_100a) only.",
+		     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+	int dev = pick_device(count);
 	CUDA_CHECK(cudaSetDevice(dev));
 	cudaDeviceProp prop;
 	CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
@@ -45,11 +59,18 @@ Context &ctx()
 	g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
 	g_ctx.verbose = g_verbose;
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-	/* keep freed blocks in the pool instead of returning them to the driver at every synchronisation */
-	cudaMemPool_t pool;
-	CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+	/* a memory pool OWNED by the library (the device's default pool is shared with every other cudaMallocAsync user of
+	 * the process and is left alone): freed blocks stay in it instead of going back to the driver at every
+	 * synchronisation; spasm_b200_trim() gives everything back */
+	cudaMemPoolProps props;
+	memset(&props, 0, sizeof(props));
+	props.allocType = cudaMemAllocationTypePinned;
+	props.handleTypes = cudaMemHandleTypeNone;
+	props.location.type = cudaMemLocationTypeDevice;
+	props.location.id = dev;
+	CUDA_CHECK(cudaMemPoolCreate(&g_pool, &props));
 	unsigned long long keep = ~0ull;
-	CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	CUDA_CHECK(cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &keep));
 	atexit([] { g_exiting = true; });      /* registered after the CUDA runtime's own handlers: runs before them */
 	return g_ctx;
 }
@@ -107,7 +128,8 @@ void *device_alloc(size_t bytes)
 			return p;
 		}
 	}
-	cudaError_t e = cudaMallocAsync(&p, bytes, ctx().stream);
+	cudaStream_t st = ctx().stream;
+	cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, g_pool, st);
 	if (e != cudaSuccess && !g_cache.empty()) {
 		/* out of memory with blocks parked in the cache: give them back and retry */
 		(void) cudaGetLastError();
@@ -116,7 +138,7 @@ void *device_alloc(size_t bytes)
 		g_cache.clear();
 		g_cache_bytes = 0;
 		CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
-		e = cudaMallocAsync(&p, bytes, ctx().stream);
+		e = cudaMallocFromPoolAsync(&p, bytes, g_pool, ctx().stream);
 	}
 	CUDA_CHECK(e);
 	return p;
@@ -213,6 +235,33 @@ void DevCsr::upload(const struct spasm_csr *A)
 
 using namespace sb;
 
+/* Creation of the primary CUDA context on a helper thread, so that it overlaps the host work that precedes the first
+ * GPU call of a one-shot tool (parsing the matrix).  Errors are ignored here: ctx() reports them.  SPASM_B200_NO_WARMUP
+ * turns it off. */
+extern "C" void spasm_b200_warmup_async(void)
+{
+	static bool started = false;
+	if (started || g_ctx.device >= 0 || getenv("SPASM_B200_NO_WARMUP"))
+		return;
+	started = true;
+	/* a program that exits without ever touching the GPU waits for the helper instead of tearing the runtime down under it */
+	atexit([] {
+		if (g_warm && g_warm->joinable())
+			g_warm->join();
+	});
+	g_warm = new std::thread([] {
+		int count = 0;
+		if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+			(void) cudaGetLastError();
+			return;
+		}
+		if (cudaSetDevice(pick_device(count)) == cudaSuccess)
+			(void) cudaFree(0);
+		(void) cudaGetLastError();
+	});
+}
+
+
 extern "C" {
 
 int spasm_b200_device_count(void)
@@ -224,6 +273,20 @@ int spasm_b200_device_count(void)
 }
 
 void spasm_b200_set_device(int device) { g_requested_device = device; }
+
+/* give the idle device memory back: the cached large blocks, then everything the library's pool holds but does not use */
+void spasm_b200_trim(void)
+{
+	if (g_ctx.device < 0)
+		return;
+	for (CachedBlock &b : g_cache)
+		cudaFreeAsync(b.ptr, g_ctx.stream);
+	g_cache.clear();
+	g_cache_bytes = 0;
+	CUDA_CHECK(cudaStreamSynchronize(g_ctx.stream));
+	if (g_pool)
+		CUDA_CHECK(cudaMemPoolTrimTo(g_pool, 0));
+}
 
 void spasm_b200_set_verbose(int verbose)
 {

@@ -91,9 +91,15 @@ static bool parse_entry(const char *s, int *i, int *j, i64 *x)
 /*
  * reference: src/spasm_io.c:59-159.  prime == -1 loads the pattern only.
  */
+/* csrc/gpu/device.cu: starts the creation of the CUDA context on a helper thread (once; no effect without a GPU) */
+void spasm_b200_warmup_async(void);
+
 struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash)
 {
 	assert(f != NULL);
+	/* a program that loads a matrix is about to echelonize it (tools/rank.c, echelonize.c, kernel.c): the CUDA context
+	 * (about a second for a fresh process) is created while the text is parsed */
+	spasm_b200_warmup_async();
 	double start = spasm_wtime();
 	struct reader r;
 	r.f = f;
