@@ -512,7 +512,7 @@ k_rref_multipliers(const i32 *__restrict__ S, int ld, int n, int c0, const Panel
 		return;
 	for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x)
 		sMinv[idx / NB][idx % NB] = info->Minv[idx / NB][idx % NB];
-	if (threadIdx.x < NB) {
+	if (threadIdx.x < k) {             /* the panel kernel wrote k entries */
 		s_prow[threadIdx.x] = info->prow[threadIdx.x];
 		s_pcol[threadIdx.x] = info->pcol[threadIdx.x];
 	}

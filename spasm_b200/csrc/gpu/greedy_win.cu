@@ -253,7 +253,7 @@ template <int K>
 __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 {
 	extern __shared__ unsigned vis[];
-	__shared__ int s_tail, s_nc;
+	__shared__ int s_tail, s_nc, s_head;
 	__shared__ int s_alive[2];
 	__shared__ int s_cand[WIN_MAXC];
 	__shared__ int ring[WIN_RING];
@@ -299,6 +299,57 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 		 * thread takes the same decisions */
 		if (head >= tail || alive <= 0)
 			break;
+		if (tail - head <= 32) {
+			/* NARROW FRONTIER (deep, thin parts of the pivot DAG: hundreds of levels late in the search): warp 0 walks
+			 * the levels on its own, one L2 round trip per level and no block barrier, for as long as the frontier
+			 * fits the warp; the other warps wait at the barrier below */
+			if (tid < 32) {
+				int h = head, t = tail, al = alive;
+				for (int rounds = 0; h < t && t - h <= 32 && al > 0 && rounds < 256; rounds++) {
+					const int j = (h + tid < t) ? ring[(h + tid) & (WIN_RING - 1)] : -1;
+					if (j >= 0) {
+						int adj[K];
+#pragma unroll
+						for (int k = 0; k < K; k += 4) {
+							const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) j * K + k);
+							adj[k] = v.x; adj[k + 1] = v.y; adj[k + 2] = v.z; adj[k + 3] = v.w;
+						}
+						if (adj[0] != -2) {
+							my_edges += 1;
+#pragma unroll
+							for (int k = 0; k < K; k++) {
+								const int c = adj[k];
+								if (c < 0)
+									continue;
+								my_edges += 1;
+								const unsigned bit = 1u << (c & 31);
+								const unsigned old = atomicOr(&vis[c >> 5], bit);
+								if (!(old & bit)) {
+									const int at = atomicAdd(&s_tail, 1);
+									ring[at & (WIN_RING - 1)] = c;
+									queue[at] = c;
+								}
+							}
+						}
+					}
+					__syncwarp();
+					h = t;
+					t = *((volatile int *) &s_tail);
+					const bool live = tid < s_nc && !(*((volatile unsigned *) &vis[s_cand[tid] >> 5]) & (1u << (s_cand[tid] & 31)));
+					al = __popc(__ballot_sync(0xffffffffu, live));
+				}
+				if (tid == 0) {
+					s_head = h;
+					s_alive[(iter + 1) & 1] = al;
+				}
+			}
+			__syncthreads();
+			head = s_head;
+			tail = s_tail;
+			alive = s_alive[(iter + 1) & 1];
+			__syncthreads();
+			continue;
+		}
 		const int cnt = min(WIN_BFS_PER * WIN_BFS_THREADS, tail - head);
 		const bool in_ring = tail - head <= WIN_RING;
 		/* up to WIN_BFS_PER frontier entries per thread: their adjacency records are loaded together (a slice costs one
@@ -396,8 +447,7 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 	constexpr int Wn = 32 * W;
 	constexpr int NWARPS = W;
 	extern __shared__ unsigned dyn[];
-	unsigned *Et = dyn;                                            /* Et[w * Wn + t]: word w of E[t] */
-	unsigned *chR = Et + (size_t) W * Wn;                          /* WIN_ECAP * W */
+	unsigned *chR = dyn;                                           /* WIN_ECAP * W */
 	unsigned *chC = chR + (size_t) WIN_ECAP * W;
 	unsigned *taken = chC + (size_t) WIN_ECAP * W;                 /* Wn * WIN_MAXC bits */
 	__shared__ int tl[1024];                                       /* surviving rows, increasing */
@@ -408,6 +458,7 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 	__shared__ unsigned s_committed[32];
 	__shared__ unsigned s_reff[2][WIN_MAXC][W], s_c0[2][WIN_MAXC][W];   /* per candidate of the current row (double-buffered) */
 	__shared__ unsigned s_hit[3];                                  /* bit k: candidate k is reached (or no candidate any more); rotated */
+	__shared__ unsigned s_Eb[2][W];                                /* E[b] of the row being resolved (double-buffered) */
 	__shared__ int s_T, s_rows;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nslots = *a.nslots;
@@ -417,10 +468,11 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 	const unsigned bal = __ballot_sync(0xffffffffu, tentative);
 	if (lane == 0)
 		s_warpcnt[warp] = __popc(bal);
-	for (int idx = tid; idx < W * Wn; idx += Wn) {
-		const int w = idx / Wn, t = idx - w * Wn;
-		Et[idx] = (w == (t >> 5)) ? (1u << (t & 31)) : 0u;
-	}
+	/* E[t], the window rows whose searches row t inherits (itself included): ONE ROW PER THREAD, IN REGISTERS */
+	unsigned Er[W];
+#pragma unroll
+	for (int w = 0; w < W; w++)
+		Er[w] = (w == (tid >> 5)) ? (1u << (tid & 31)) : 0u;
 	for (int idx = tid; idx < (Wn * WIN_MAXC) / 32; idx += Wn)
 		taken[idx] = 0;
 	if (tid < 32)
@@ -444,6 +496,11 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 	const int T = s_T;
 	int mypick = -1;
 	int iter = 0;                       /* the per-row scratch is double-buffered: a slow warp may still read the previous row's */
+	if (T > 0 && tid == tl[0]) {
+#pragma unroll
+		for (int w = 0; w < W; w++)
+			s_Eb[0][w] = Er[w];
+	}
 	for (int base = 0; base < T;) {
 		/* ---- stage the vectors of the next rows (as many rows as fit WIN_ECAP entries) */
 		if (tid == 0) {
@@ -481,6 +538,13 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 			 * barrier of the previous row, and its next writers come after the barrier below */
 			if (tid == 0)
 				s_hit[(iter + 1) % 3] = 0;
+			/* the row resolved next publishes its E row now (rewritten below if this row commits and changes it) */
+			const int bnext = (base + r + 1 < T) ? tl[base + r + 1] : -1;
+			if (tid == bnext) {
+#pragma unroll
+				for (int w = 0; w < W; w++)
+					s_Eb[pb ^ 1][w] = Er[w];
+			}
 			/* one warp per candidate entry: is it reached by row b or by a search row b inherits? */
 			for (int k = warp; k < nc; k += NWARPS) {
 				const int v = ch_vec[off + k];
@@ -489,7 +553,7 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 				if (lane < W) {
 					cv = chC[(off + k) * W + lane];
 					reff = chR[(off + k) * W + lane] | (cv & s_committed[lane]);
-					Ev = Et[lane * Wn + b];
+					Ev = s_Eb[pb][lane];
 					s_reff[pb][k][lane] = reff;
 					s_c0[pb][k][lane] = cv;
 				}
@@ -508,11 +572,16 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 				bool hit = (s_c0[pb][pick][tid >> 5] >> (tid & 31)) & 1u;
 #pragma unroll
 				for (int w = 0; w < W; w++)
-					hit |= (Et[w * Wn + tid] & s_reff[pb][pick][w]) != 0;
+					hit |= (Er[w] & s_reff[pb][pick][w]) != 0;
 				if (hit) {
 #pragma unroll
 					for (int w = 0; w < W; w++)
-						Et[w * Wn + tid] |= Et[w * Wn + b];
+						Er[w] |= s_Eb[pb][w];
+					if (tid == bnext) {
+#pragma unroll
+						for (int w = 0; w < W; w++)
+							s_Eb[pb ^ 1][w] = Er[w];
+					}
 				}
 			}
 			if (tid == b)
@@ -660,7 +729,7 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.Rvec = Rvec.ptr;
 	a.Cvec = Cvec.ptr;
 	a.queues = queues.ptr;
-	const size_t res_smem = ((size_t) a.W * Wn + 2 * (size_t) WIN_ECAP * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
+	const size_t res_smem = (2 * (size_t) WIN_ECAP * a.W + (size_t) Wn * WIN_MAXC / 32) * sizeof(unsigned);
 	const int max_windows = (a.nlist + Wn - 1) / Wn;
 #define WIN_DISPATCH(KK)                                                   \
 	do {                                                                   \

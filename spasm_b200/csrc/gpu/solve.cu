@@ -812,10 +812,11 @@ __global__ void __launch_bounds__(1024)
 k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                     const i64 *__restrict__ rptr, const int *__restrict__ rdst,
                     int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
-                    int4 *X, int ld4, int R4, Zp F, int *level_out)
+                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats)
 {
 	__shared__ int s_node, s_next;
 	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
+	unsigned n_certain = 0, n_released = 0, n_polled = 0;      /* how the CTA came by its columns (thread 0; development) */
 	__shared__ FlowPub pub;
 	const int tid = threadIdx.x, lane = tid & 31;
 	const int T3 = blockDim.x - 64;                       /* compute threads */
@@ -862,8 +863,15 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 			}
 			__syncthreads();
 			const int c0 = s_node;
-			if (c0 < 0)
+			if (c0 < 0) {
+				if (tid == 0 && hopstats) {
+					atomicAdd(&hopstats[0], (unsigned long long) n_certain);
+					atomicAdd(&hopstats[1], (unsigned long long) n_released);
+					atomicAdd(&hopstats[2], (unsigned long long) n_polled);
+				}
 				return;
+			}
+			n_polled++;
 			const i64 e0 = ptr[c0];
 			const int cnt = (int) (ptr[c0 + 1] - e0);
 			if (tid < FLOW_MAXE && tid < cnt) {
@@ -1001,6 +1009,8 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 		}
 		__syncthreads();                                  /* [C] */
 		int nxt = s_next;
+		if (nxt >= 0)
+			n_certain++;
 		if (nxt < 0) {
 			/* nobody is certain: publish now, keep a dependent the decrements release (if any) */
 			if (is_publish) {
@@ -1010,6 +1020,8 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 			}
 			__syncthreads();
 			nxt = s_next;
+			if (nxt >= 0)
+				n_released++;
 		}
 		if (nxt >= 0) {
 			const FlowMeta2 *nx = &dep[buf][nxt];
@@ -1220,6 +1232,9 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		if (flow2) {
 			threads = R4 + 64 > 512 ? 1024 : R4 + 64 > 256 ? 512 : 256;
 			DevBuf<int> doneflag((size_t) n);
+			static const bool hoptrace = getenv("SPASM_B200_TRACE") != NULL;
+			DevBuf<unsigned long long> hopstats(3);
+			hopstats.zero(s);
 			k_flow2_flags<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr.ptr, doneflag.ptr);
 			int occ = 0;
 			CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow2, threads, 0));
@@ -1227,10 +1242,17 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			tk.start();
 			k_panel_solve_flow2<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
 			                                          G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3, doneflag.ptr,
-			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr);
+			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr, hoptrace ? hopstats.ptr : nullptr);
 			LAUNCHED(2);
 			KERNEL_CHECK();
 			stats().pub.ms_k_panel_solve += tk.stop_ms();      /* before doneflag goes out of scope: the stop synchronises */
+			if (hoptrace) {
+				unsigned long long h3[3];
+				CUDA_CHECK(cudaMemcpyAsync(h3, hopstats.ptr, sizeof(h3), cudaMemcpyDeviceToHost, s));
+				sync();
+				fprintf(stderr, "[trace]     dataflow solve: %d columns, R = %d; continued with a certain dependent %llu times, with a released one %llu, polled the queue %llu\n",
+				        G.nscheduled, R, h3[0], h3[1], h3[2]);
+			}
 		} else {
 		int occ = 0;
 		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow, threads, 0));

@@ -28,7 +28,7 @@ def test_compute_sanitizer_reports_no_error(tool):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"sanitizer_{tool}.txt"), "w") as f:
         f.write(" ".join(cmd) + "\n" + text[-20000:])
-    m = re.search(r"ERROR SUMMARY: (\d+) error", text)
+    m = re.search(r"ERROR SUMMARY: (\d+) error", text) or re.search(r"RACECHECK SUMMARY: (\d+) hazard", text)
     assert m, text[-3000:]
     assert int(m.group(1)) == 0 and out.returncode == 0, text[-3000:]
     assert text.count(" rank ") >= 6, "the workload did not run to the end:\n" + text[-2000:]
