@@ -105,6 +105,21 @@ PROTOTYPES = {
     "spasm_transpose": (CsrP, [CsrP, C.c_int]),
     "spasm_xApy": (None, [i32_p, CsrP, i32_p]),
     "spasm_Axpy": (None, [CsrP, i32_p, i32_p]),
+    # small-grain host verifiers (csrc/host/verify.c; reference: src/spasm.h:199-223, :268)
+    "spasm_scatter": (None, [CsrP, C.c_int, i32, i32_p]),
+    "spasm_dfs": (C.c_int, [C.c_int, CsrP, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "spasm_reach": (C.c_int, [CsrP, CsrP, C.c_int, C.c_int, c_int_p, c_int_p]),
+    "spasm_sparse_triangular_solve": (C.c_int, [CsrP, CsrP, C.c_int, c_int_p, i32_p, c_int_p]),
+    "spasm_dense_back_solve": (None, [CsrP, i32_p, i32_p, c_int_p]),
+    "spasm_dense_forward_solve": (C.c_bool, [CsrP, i32_p, i32_p, c_int_p]),
+    "spasm_pvec": (None, [c_int_p, i32_p, i32_p, C.c_int]),
+    "spasm_ipvec": (None, [c_int_p, i32_p, i32_p, C.c_int]),
+    "spasm_pinv": (c_int_p, [c_int_p, C.c_int]),
+    "spasm_permute": (CsrP, [CsrP, c_int_p, c_int_p, C.c_int]),
+    "spasm_random_permutation": (c_int_p, [C.c_int]),
+    "spasm_range_pvec": (None, [c_int_p, C.c_int, C.c_int, c_int_p]),
+    "spasm_submatrix": (CsrP, [CsrP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spasm_kernel_from_rref": (CsrP, [CsrP, c_int_p]),
     "spasm_pivots_extract_structural": (C.c_int, [CsrP, c_int_p, LuP, c_int_p, OptsP]),
     "spasm_schur_estimate_density": (C.c_double, [CsrP, c_int_p, C.c_int, CsrP, c_int_p, C.c_int]),
     "spasm_schur": (CsrP, [CsrP, c_int_p, C.c_int, LuP, C.c_double, TripletP, c_int_p, c_int_p]),

@@ -122,6 +122,19 @@ k_gemm_sub(i32 *__restrict__ C, int ldc, const i32 *__restrict__ A, int lda, con
 	}
 }
 
+static void gemm_sub_on(cudaStream_t st, i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F, const int *d_K)
+{
+	if (M <= 0 || N <= 0 || K <= 0)
+		return;
+	dim3 grid(cdiv(N, GN), cdiv(M, GM));
+	const bool small = F.p <= 46337 && (i64) K < (i64) F.delay;
+	if (small)
+		k_gemm_sub<true><<<grid, 256, 0, st>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
+	else
+		k_gemm_sub<false><<<grid, 256, 0, st>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
+	LAUNCHED(1);
+}
+
 void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ldb, int M, int N, int K, const Zp &F, const int *d_K)
 {
 	if (M <= 0 || N <= 0 || K <= 0)
@@ -142,9 +155,8 @@ void dense_gemm_sub(i32 *C, int ldc, const i32 *A, int lda, const i32 *B, int ld
 		k_gemm_sub<false><<<grid, 256, 0, ctx().stream>>>(C, ldc, A, lda, B, ldb, M, N, K, F, d_K);
 	LAUNCHED(1);
 	KERNEL_CHECK();
-	/* the rank-<=32 trailing updates of the panels (d_K: the rank is only known on the device) are counted at the panel
-	 * width, an upper bound that is exact for full-rank panels: they are dense work too, executed on CUDA cores */
-	stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
+	if (!d_K)      /* the rank-<=32 trailing updates of a block are counted once, as 2 n m rank, at the end of dense_rref */
+		stats().pub.gemm_fieldops += 2.0 * M * (double) N * K;
 }
 
 /* ================================================================== gathers */
@@ -578,21 +590,67 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 	const bool use_cluster = !single && n >= 256 && cluster_smem <= 160 * 1024;
 	if (use_cluster)
 		CUDA_CHECK(cudaFuncSetAttribute(k_rref_panel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cluster_smem));
+	/* LOOK-AHEAD.  The factorisation of a panel occupies 8 SMs for ~120 us and only needs its own 32 columns up to
+	 * date; the rank-32 update of everything to the right of it (S[:, c0:] -= W * S[pivot rows, c0:]) occupies the rest
+	 * of the GPU.  So the update of panel p is split: the columns of panel p and p+1 on the main stream (they gate
+	 * panel p+1), the rest on a second stream, where it overlaps the factorisation of panel p+1:
+	 *     main: P(p) M(p) | wait G2(p-1) | C1(p) G1(p)            aux: wait M(p) | C2(p) G2(p)
+	 * W, the pivot-row copy and the panel record are double-buffered (G2(p) reads them while panel p+1 is written).
+	 * Same arithmetic in the same order on every entry (the two updates of an entry stay ordered by the events). */
+	static const bool no_ahead = getenv("SPASM_B200_NO_LOOKAHEAD") != NULL;
+	static cudaStream_t s2 = nullptr;
+	static cudaEvent_t ev_m[2] = {nullptr, nullptr}, ev_g2[2] = {nullptr, nullptr};
+	if (!s2) {
+		CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+		for (int k = 0; k < 2; k++) {
+			CUDA_CHECK(cudaEventCreateWithFlags(&ev_m[k], cudaEventDisableTiming));
+			CUDA_CHECK(cudaEventCreateWithFlags(&ev_g2[k], cudaEventDisableTiming));
+		}
+	}
+	DevBuf<i32> W2((size_t) n * NB), P2((size_t) NB * (size_t) m);
+	DevBuf<PanelInfo> info2(1);
+	i32 *Wb[2] = {W.ptr, W2.ptr}, *Pb[2] = {P.ptr, P2.ptr};
+	PanelInfo *ib[2] = {info.ptr, info2.ptr};
+	/* everything queued on the main stream so far (the block itself) precedes the first use of the second stream */
+	CUDA_CHECK(cudaEventRecord(ev_g2[1], s));
+	CUDA_CHECK(cudaStreamWaitEvent(s2, ev_g2[1], 0));
 	int panels = 0;
+	bool g2_pending = false;
 	for (int c0 = 0; c0 < m; c0 += NB) {
-		int width = m - c0;
+		const int width = m - c0;
+		const int b = panels & 1;
 		if (use_cluster)
-			k_rref_panel_cluster<<<PC_CTAS, PC_THREADS, cluster_smem, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, info.ptr, chunk, F);
+			k_rref_panel_cluster<<<PC_CTAS, PC_THREADS, cluster_smem, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, ib[b], chunk, F);
 		else
-			k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, W.ptr, info.ptr, scratch.ptr, use_smem, F);
-		k_rref_multipliers<<<std::min(cdiv(n, 8), 148u * 4), 256, 0, s>>>(S, ld, n, c0, info.ptr, W.ptr, F);
-		dim3 g(cdiv(width, 256), NB);
-		k_copy_pivot_rows<<<g, 256, 0, s>>>(S, ld, c0, width, info.ptr, P.ptr, m);
-		LAUNCHED(3);
-		dense_gemm_sub(S + c0, ld, W.ptr, NB, P.ptr, m, n, width, NB, F, &info.ptr->k);
+			k_rref_panel<<<1, 1024, use_smem ? need : 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, Wb[b], ib[b], scratch.ptr, use_smem, F);
+		k_rref_multipliers<<<std::min(cdiv(n, 8), 148u * 4), 256, 0, s>>>(S, ld, n, c0, ib[b], Wb[b], F);
+		LAUNCHED(2);
+		const int near = no_ahead ? width : std::min(width, 2 * NB);      /* columns that gate the next panel */
+		if (near < width) {
+			CUDA_CHECK(cudaEventRecord(ev_m[b], s));
+			CUDA_CHECK(cudaStreamWaitEvent(s2, ev_m[b], 0));
+			dim3 g2(cdiv(width - near, 256), NB);
+			k_copy_pivot_rows<<<g2, 256, 0, s2>>>(S, ld, c0 + near, width - near, ib[b], Pb[b] + near, m);
+			LAUNCHED(1);
+		}
+		if (g2_pending)                       /* the far update of the previous panel touched the near columns too */
+			CUDA_CHECK(cudaStreamWaitEvent(s, ev_g2[b ^ 1], 0));
+		dim3 g1(cdiv(near, 256), NB);
+		k_copy_pivot_rows<<<g1, 256, 0, s>>>(S, ld, c0, near, ib[b], Pb[b], m);
+		LAUNCHED(1);
+		gemm_sub_on(s, S + c0, ld, Wb[b], NB, Pb[b], m, n, near, NB, F, &ib[b]->k);
+		g2_pending = false;
+		if (near < width) {
+			gemm_sub_on(s2, S + c0 + near, ld, Wb[b], NB, Pb[b] + near, m, n, width - near, NB, F, &ib[b]->k);
+			CUDA_CHECK(cudaEventRecord(ev_g2[b], s2));
+			g2_pending = true;
+		}
 		if (++panels % 8 == 0 && fetch(rank_dev.ptr) >= n)
 			break;
 	}
+	/* the far updates rejoin the main stream */
+	CUDA_CHECK(cudaEventRecord(ev_g2[0], s2));
+	CUDA_CHECK(cudaStreamWaitEvent(s, ev_g2[0], 0));
 	KERNEL_CHECK();
 	out.rank = fetch(rank_dev.ptr);
 	out.pivcol.resize(out.rank);

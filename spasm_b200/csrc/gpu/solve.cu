@@ -771,12 +771,47 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
  * (as before), or polls the queue.  Each column is still written once, from final columns: same values.
  * Needs one right-hand-side group per compute thread (R4 <= blockDim.x - 64); wider batches take the first version.
  */
-struct FlowMeta2 {
+struct FlowMeta2 {             /* 24 ints = 96 bytes: one dependent of a column in the per-column blob (see k_flow2_blob) */
 	int node, cnt, ready, pad;
 	i64 e0, rb, re;
 	int src[FLOW_MAXE];
 	i32 val[FLOW_MAXE];
 };
+static_assert(sizeof(FlowMeta2) == 88 + 8 || sizeof(FlowMeta2) == 104, "FlowMeta2 layout");
+#define FLOW2_WORDS ((int) (sizeof(FlowMeta2) / sizeof(int)))
+
+/* blob[c] = the FlowMeta2 records of the first FLOW_MAXD dependents of column c (their dependency lists and their own
+ * ranges of dependents), contiguous: the prefetch of a hop is ONE coalesced copy instead of a chain of four dependent
+ * loads (rdst -> ptr/rptr -> src/val) */
+__global__ void k_flow2_blob(int n, const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
+                             const i64 *__restrict__ rptr, const int *__restrict__ rdst, FlowMeta2 *blob)
+{
+	const i64 item = (i64) blockIdx.x * blockDim.x + threadIdx.x;
+	const int c = (int) (item / FLOW_MAXD), di = (int) (item % FLOW_MAXD);
+	if (c >= n)
+		return;
+	FlowMeta2 m;
+	m.node = -1; m.cnt = 0; m.ready = 0; m.pad = 0; m.e0 = 0; m.rb = 0; m.re = 0;
+#pragma unroll
+	for (int e = 0; e < FLOW_MAXE; e++) {
+		m.src[e] = -1;
+		m.val[e] = 0;
+	}
+	const i64 rb = rptr[c], re = rptr[c + 1];
+	if (rb + di < re) {
+		const int d = rdst[rb + di];
+		m.node = d;
+		m.e0 = ptr[d];
+		m.cnt = (int) (ptr[d + 1] - m.e0);
+		m.rb = rptr[d];
+		m.re = rptr[d + 1];
+		for (int e = 0; e < FLOW_MAXE && e < m.cnt; e++) {
+			m.src[e] = src[m.e0 + e];
+			m.val[e] = val[m.e0 + e];
+		}
+	}
+	blob[(size_t) c * FLOW_MAXD + di] = m;
+}
 
 struct FlowPub {
 	int valid, node, buf, skip;
@@ -812,7 +847,7 @@ __global__ void __launch_bounds__(1024)
 k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                     const i64 *__restrict__ rptr, const int *__restrict__ rdst,
                     int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
-                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats)
+                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob)
 {
 	__shared__ int s_node, s_next;
 	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
@@ -952,29 +987,26 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				level_out[c] = lv + 1;
 			}
 		} else if (is_prefetch) {
-			/* ---- 2b. metadata of the dependents of c, and whether c is the last dependency they wait for */
+			/* ---- 2b. metadata of the dependents of c (one coalesced copy of the column's blob), and whether c is the
+			 * last dependency they wait for (the flags of their other dependencies) */
 			FlowMeta2 *dp = dep[buf];
+			{
+				const int *gsrc = reinterpret_cast<const int *>(blob + (size_t) c * FLOW_MAXD);
+				int *gdst = reinterpret_cast<int *>(dp);
+#pragma unroll
+				for (int w = lane; w < FLOW_MAXD * FLOW2_WORDS; w += 32)
+					gdst[w] = gsrc[w];
+			}
+			__syncwarp();
 			for (int pass = 0; pass < (FLOW_MAXD * FLOW_MAXE) / 32; pass++) {
 				const int item = pass * 32 + lane;
 				const int di = item / FLOW_MAXE, ei = item % FLOW_MAXE;
 				bool ok = true;                       /* this dependency does not stand in the way */
-				int dcnt = 0;
-				if (rb + di < re) {
-					const int d = rdst[rb + di];
-					const i64 de0 = ptr[d];
-					dcnt = (int) (ptr[d + 1] - de0);
+				const int dcnt = dp[di].cnt;
+				if (dp[di].node >= 0) {
 					if (ei < dcnt) {
-						const int sc = src[de0 + ei];
-						dp[di].src[ei] = sc;
-						dp[di].val[ei] = val[de0 + ei];
+						const int sc = dp[di].src[ei];
 						ok = (sc == c) || (*((volatile int *) &doneflag[sc]) != 0);
-					}
-					if (ei == 0) {
-						dp[di].node = d;
-						dp[di].cnt = dcnt;
-						dp[di].e0 = de0;
-						dp[di].rb = rptr[d];
-						dp[di].re = rptr[d + 1];
 					}
 				} else {
 					ok = false;
@@ -982,7 +1014,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				const unsigned okmask = __ballot_sync(0xffffffffu, ok);
 				if (ei == 0) {
 					const unsigned mine = (okmask >> (lane & ~(FLOW_MAXE - 1))) & ((1u << FLOW_MAXE) - 1);
-					dp[di].ready = (rb + di < re) && dcnt <= FLOW_MAXE && mine == ((1u << FLOW_MAXE) - 1);
+					dp[di].ready = dp[di].node >= 0 && dcnt <= FLOW_MAXE && mine == ((1u << FLOW_MAXE) - 1);
 				}
 			}
 			__threadfence();                          /* flags read before the panel vectors of those columns are */
@@ -1235,6 +1267,9 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			static const bool hoptrace = getenv("SPASM_B200_TRACE") != NULL;
 			DevBuf<unsigned long long> hopstats(3);
 			hopstats.zero(s);
+			DevBuf<char> blob((size_t) n * FLOW_MAXD * sizeof(FlowMeta2));
+			k_flow2_blob<<<cdiv((size_t) n * FLOW_MAXD, 256), 256, 0, s>>>(n, G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, (FlowMeta2 *) blob.ptr);
+			LAUNCHED(1);
 			k_flow2_flags<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr.ptr, doneflag.ptr);
 			int occ = 0;
 			CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_panel_solve_flow2, threads, 0));
@@ -1242,7 +1277,8 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			tk.start();
 			k_panel_solve_flow2<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
 			                                          G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3, doneflag.ptr,
-			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr, hoptrace ? hopstats.ptr : nullptr);
+			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr, hoptrace ? hopstats.ptr : nullptr,
+			                                          (const FlowMeta2 *) blob.ptr);
 			LAUNCHED(2);
 			KERNEL_CHECK();
 			stats().pub.ms_k_panel_solve += tk.stop_ms();      /* before doneflag goes out of scope: the stop synchronises */

@@ -40,7 +40,7 @@ CASES = {
     "config3@0.25": ("config3", 0.25, {"sparsity_threshold": 0.01}, "identity"),
     "config3@0.5": ("config3", 0.5, {"sparsity_threshold": 0.01}, "identity"),
 }
-OUT = os.path.join(HERE, "golden_fullsize.json")
+OUT = os.environ.get("GOLDEN_OUT", os.path.join(HERE, "golden_fullsize.json"))     # several generators in parallel: one file each, merged by hand
 
 
 def identity_hash(m: int, prime: int) -> str:

@@ -233,3 +233,36 @@ def test_sha256_matches_hashlib_for_every_length_and_chunking(product):
         out = C.create_string_buffer(32)
         product.spasm_SHA256_final(out, ctx)
         assert out.raw == hashlib.sha256(data).digest(), n
+
+
+def test_host_verifiers_equal_the_reference_row_by_row():
+    """csrc/host/verify.c against the reference's own functions (oracle/_ref) on the same echelon form: the one-row
+    sparse triangular solve must return the same pattern IN THE SAME ORDER (reach = DFS post-order, src/spasm_reach.c)
+    and the same values; permutations, sub-matrix and kernel_from_rref the same arrays."""
+    import oracle
+    R_ = oracle.ref()
+    if R_ is None:
+        pytest.skip("oracle/_ref not built")
+    from spasm_b200 import abi, host, synthetic
+    L = spasm_b200.lib()
+    t = synthetic.config1(0.02)
+    e = oracle.echelonize(oracle.compress(t), oracle.default_opts())
+    U, qinv = e.U, np.ascontiguousarray(e.qinv, np.int32)
+    m = U["m"]
+    out = {}
+    for tag, lib_ in (("ref", R_), ("b200", L)):
+        Uh, Ah = host.from_numpy(lib_, U), host.compress(lib_, t)
+        rows = []
+        xj = np.zeros(3 * m, np.int32)
+        x = np.zeros(m, np.int32)
+        for k in range(0, Ah.n, 7):
+            top = lib_.spasm_sparse_triangular_solve(Uh.ptr, Ah.ptr, k, abi.as_int_p(xj), abi.as_i32_p(x), abi.as_int_p(qinv))
+            pat = xj[top:m].copy()
+            rows.append((top, pat.tobytes(), x[pat].tobytes()))
+        perm = np.random.default_rng(5).permutation(Ah.n).astype(np.int32)
+        pinv_ptr = lib_.spasm_pinv(abi.as_int_p(perm), Ah.n)
+        pinv = np.ctypeslib.as_array(pinv_ptr, shape=(Ah.n,)).copy()
+        Pm = host.CsrHandle(lib_, lib_.spasm_permute(Ah.ptr, abi.as_int_p(perm), None, 1)).numpy()
+        Sm = host.CsrHandle(lib_, lib_.spasm_submatrix(Ah.ptr, 3, Ah.n // 2, 5, Ah.m - 7, 1)).numpy()
+        out[tag] = (rows, pinv.tobytes(), tuple(Pm[k].tobytes() for k in "pjx"), tuple(Sm[k].tobytes() for k in "pjx"))
+    assert out["ref"] == out["b200"]
