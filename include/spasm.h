@@ -3,9 +3,26 @@
  *
  * This header is the drop-in boundary: it declares the same types and entry
  * points, with the same memory layout, as SpaSM's public header
- * (reference: src/spasm.h).  Programs written against the reference (its
- * tools/rank.c, tools/echelonize.c, tools/kernel.c and its tests) compile
- * against this file and link against libspasm_b200.so unchanged.
+ * (reference: src/spasm.h).  Programs written against the reference compile
+ * against this file and link against libspasm_b200.so unchanged: its
+ * tools/rank.c, tools/echelonize.c, tools/kernel.c, and its test programs
+ * echelonize, kernel, schur, schur_dense, dense_rref_ffpack, sparse_utsolve,
+ * sparse_usolve, dense_usolve, GFp, prng, sha, spmv, submatrix, transpose,
+ * mat_perm, vec_perm (oracle/Makefile: b200_tools, b200_tests).
+ *
+ * NOT provided (22 symbols of the reference's header are reduced to 8):
+ *   - declared here, exported, but aborting with errx(1, ...): spasm_solve,
+ *     spasm_gesv, the rank-certificate functions, spasm_factorization_verify,
+ *     spasm_ffpack_LU, and opts->L / opts->complete in spasm_echelonize (the
+ *     PLUQ path) -- tools/solve, rank --certificate, the
+ *     reference tests lu / solve / gesv / rank_cert / dense_lu_ffpack link but
+ *     do not run;
+ *   - neither declared nor exported: spasm_dulmage_mendelsohn,
+ *     spasm_maximum_matching, spasm_strongly_connected_components,
+ *     spasm_structural_rank, spasm_submatching, spasm_permute_row_matching,
+ *     spasm_permute_column_matching, spasm_save_pnm (independent graph library
+ *     and bitmap output, never called by the echelonization) -- tools/dm,
+ *     tools/bitmap and the tests dm / matching / scc do not link.
  *
  * What differs is behind the boundary: spasm_echelonize(), spasm_rref(),
  * spasm_kernel(), the spasm_schur*() family, spasm_pivots_extract_structural()
