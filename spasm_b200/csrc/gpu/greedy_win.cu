@@ -700,6 +700,16 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.nlist = fetch(off_.ptr + n);
 	if (a.nlist == 0)
 		return true;
+	/* Which formulation?  Measured on the BASELINE shapes: with short rows (3-5 entries: configs 1, 2, 4, 5) most
+	 * searching rows commit and the windows win or tie (config 1: 6.0 vs 7.8 ms, config 2: 57 vs 54 ms) without any
+	 * spin-wait; with 11 entries per row (config 3) 96 % of the searches fail after visiting two thirds of the graph, the
+	 * work is pure traversal throughput and the journal kernel keeps more rows in flight (109 vs 189 ms). */
+	{
+		static const bool force = getenv("SPASM_B200_GREEDY_WINDOW") != NULL;
+		const double avg_len = (double) A.nnz / std::max(1, n);
+		if (!force && avg_len > 6.0)
+			return false;
+	}
 	DevBuf<int> lrow((size_t) a.nlist * WIN_MAXC);
 	k_win_list_rows<<<cdiv(n, 256), 256, 0, s>>>(n, flag.ptr, off_.ptr, A.p, A.j, list.ptr, lrow.ptr);
 	LAUNCHED(1);

@@ -849,7 +849,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
                     int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
                     int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob)
 {
-	__shared__ int s_node, s_next;
+	__shared__ int s_node, s_next, s_capt;
 	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
 	unsigned n_certain = 0, n_released = 0, n_polled = 0;      /* how the CTA came by its columns (thread 0; development) */
 	__shared__ FlowPub pub;
@@ -1021,7 +1021,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 		} else if (is_publish) {
 			/* ---- 2c. publication of the previous column of the chain (deferred by one hop) */
 			if (pub.valid)
-				flow2_publish(pub, dep[pub.buf], rdst, pending, queue, tail, done, doneflag, &s_next, false, lane);
+				flow2_publish(pub, dep[pub.buf], rdst, pending, queue, tail, done, doneflag, &s_capt, false, lane);
 		}
 		__syncthreads();                                  /* [B] */
 		/* ---- 3. go on with a dependent that is certain to be released by c, if there is one */
@@ -1032,6 +1032,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				if (dep[buf][di].ready)
 					pick = di;
 			s_next = pick;
+			s_capt = -1;                     /* written by the capture of an immediate publication only, read after its barrier */
 			pub.valid = pick >= 0;
 			pub.node = c;
 			pub.buf = buf;
@@ -1048,10 +1049,10 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 			if (is_publish) {
 				FlowPub now;
 				now.valid = 1; now.node = c; now.buf = buf; now.skip = -1; now.rb = rb; now.re = re;
-				flow2_publish(now, dep[buf], rdst, pending, queue, tail, done, doneflag, &s_next, true, lane);
+				flow2_publish(now, dep[buf], rdst, pending, queue, tail, done, doneflag, &s_capt, true, lane);
 			}
 			__syncthreads();
-			nxt = s_next;
+			nxt = s_capt;
 			if (nxt >= 0)
 				n_released++;
 		}
