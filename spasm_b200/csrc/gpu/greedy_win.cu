@@ -39,6 +39,7 @@ namespace sb {
 #define WIN_ECAP 256           /* candidate entries whose vectors are staged in shared memory at a time (phase B) */
 #define WIN_BFS_THREADS 256
 #define WIN_BFS_PER 4            /* frontier entries per thread and slice (phase A) */
+#define WIN_CHASE 6              /* hops a thread follows on its own before the next slice */
 #define WIN_RING 4096          /* frontier ring in shared memory (phase A); the global queue holds everything */
 
 struct WinArgs {
@@ -363,36 +364,52 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 		}
 		__syncthreads();
 		if (js[0] >= 0) {
-			int adj[WIN_BFS_PER][K];
+			/* CHASE: of the columns an entry discovers, the thread keeps the first one for itself and expands it in the
+			 * next round (up to WIN_CHASE rounds) instead of pushing it: a thin chain of the pivot DAG is then walked by
+			 * one thread with one L2 round trip per hop, not one slice (three block barriers) per hop.  The order of a
+			 * search does not matter, only the set it reaches. */
+			for (int round = 0; round <= WIN_CHASE; round++) {
+				int adj[WIN_BFS_PER][K];
+				bool any = false;
 #pragma unroll
-			for (int u = 0; u < WIN_BFS_PER; u++) {
-				if (js[u] >= 0) {
+				for (int u = 0; u < WIN_BFS_PER; u++) {
+					if (js[u] >= 0) {
+						any = true;
 #pragma unroll
-					for (int k = 0; k < K; k += 4) {
-						const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) js[u] * K + k);
-						adj[u][k] = v.x; adj[u][k + 1] = v.y; adj[u][k + 2] = v.z; adj[u][k + 3] = v.w;
+						for (int k = 0; k < K; k += 4) {
+							const int4 v = *reinterpret_cast<const int4 *>(a.padj + (size_t) js[u] * K + k);
+							adj[u][k] = v.x; adj[u][k + 1] = v.y; adj[u][k + 2] = v.z; adj[u][k + 3] = v.w;
+						}
+					} else {
+						adj[u][0] = -2;
 					}
-				} else {
-					adj[u][0] = -2;
 				}
-			}
+				if (!any)
+					break;
+				const bool last = round == WIN_CHASE;
 #pragma unroll
-			for (int u = 0; u < WIN_BFS_PER; u++) {
-				if (adj[u][0] == -2)
-					continue;
-				my_edges += 1;
-#pragma unroll
-				for (int k = 0; k < K; k++) {
-					const int c = adj[u][k];
-					if (c < 0)
+				for (int u = 0; u < WIN_BFS_PER; u++) {
+					js[u] = -1;
+					if (adj[u][0] == -2)
 						continue;
 					my_edges += 1;
-					const unsigned bit = 1u << (c & 31);
-					const unsigned old = atomicOr(&vis[c >> 5], bit);
-					if (!(old & bit)) {
-						const int at = atomicAdd(&s_tail, 1);
-						ring[at & (WIN_RING - 1)] = c;
-						queue[at] = c;
+#pragma unroll
+					for (int k = 0; k < K; k++) {
+						const int c = adj[u][k];
+						if (c < 0)
+							continue;
+						my_edges += 1;
+						const unsigned bit = 1u << (c & 31);
+						const unsigned old = atomicOr(&vis[c >> 5], bit);
+						if (!(old & bit)) {
+							if (js[u] < 0 && !last) {
+								js[u] = c;                  /* kept: expanded by this thread in the next round */
+							} else {
+								const int at = atomicAdd(&s_tail, 1);
+								ring[at & (WIN_RING - 1)] = c;
+								queue[at] = c;
+							}
+						}
 					}
 				}
 			}
