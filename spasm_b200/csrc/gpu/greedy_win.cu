@@ -48,7 +48,9 @@ struct WinArgs {
 	const i64 *Ap;
 	const int *Aj;
 	int *qinv, *pinv;
-	int *padj;                 /* m * K: the other entries of the pivot row of column j; [0] == -2: not pivotal */
+	int *padj;                 /* m * K: the other entries of the pivot row of column j; [0] == -2: not pivotal; a last
+	                            * slot <= -16 links to an overflow record of 16 more entries (rows longer than K + 1) */
+	int *ovf, *novf;           /* overflow records, bump counter */
 	const int *list;           /* candidate rows after FL / FL on columns, increasing */
 	const int *lrow;           /* nlist * WIN_MAXC: their entries, padded with -1 */
 	int nlist;
@@ -68,31 +70,90 @@ struct WinArgs {
 
 /* ------------------------------------------------------------------ adjacency records */
 
+#define WIN_OVF 16             /* entries of an overflow record */
+
+/* adjacency record of pivot column j from the entries of its row (ent[0:n), -1 = hole): the other columns, the first
+ * K - 1 (or K when they all fit) inline, the rest in an overflow record linked from the last slot */
 template <int K>
-__global__ void k_win_padj_init(int m, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ qinv, int *padj)
+__device__ __forceinline__ void win_build_record(const int *ent, int n, int j, int *rec, int *ovf, int *novf)
+{
+	int others = 0;
+	for (int k = 0; k < n; k++)
+		others += (ent[k] >= 0 && ent[k] != j);
+	const bool spill = others > K;
+	int cnt = 0, o = -1, ocnt = 0;
+	if (spill)
+		o = atomicAdd(novf, 1);
+	for (int k = 0; k < n; k++) {
+		const int c = ent[k];
+		if (c < 0 || c == j)
+			continue;
+		if (!spill || cnt < K - 1)
+			rec[cnt++] = c;
+		else if (ocnt < WIN_OVF)
+			ovf[(size_t) o * WIN_OVF + ocnt++] = c;
+	}
+	if (spill) {
+		for (; ocnt < WIN_OVF; ocnt++)
+			ovf[(size_t) o * WIN_OVF + ocnt] = -1;
+		rec[K - 1] = -(16 + o);
+	} else {
+		for (; cnt < K; cnt++)
+			rec[cnt] = -1;
+	}
+}
+
+template <int K>
+__global__ void k_win_padj_init(int m, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ qinv, int *padj,
+                                int *ovf, int *novf)
 {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= m)
 		return;
-	int out[K];
-#pragma unroll
-	for (int k = 0; k < K; k++)
-		out[k] = -1;
-	int I = qinv[j];
+	int *rec = padj + (size_t) j * K;
+	const int I = qinv[j];
 	if (I < 0) {
-		out[0] = -2;
-	} else {
-		int cnt = 0;
-		for (i64 e = Ap[I]; e < Ap[I + 1]; e++) {
-			int c = Aj[e];
-			if (c != j && cnt < K)
-				out[cnt++] = c;
-		}
+		rec[0] = -2;
+		for (int k = 1; k < K; k++)
+			rec[k] = -1;
+		return;
 	}
-#pragma unroll
-	for (int k = 0; k < K; k += 4)
-		*reinterpret_cast<int4 *>(padj + (size_t) j * K + k) = make_int4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+	int ent[WIN_MAXC];
+	int n = 0;
+	for (i64 e = Ap[I]; e < Ap[I + 1] && n < WIN_MAXC; e++)
+		ent[n++] = Aj[e];
+	win_build_record<K>(ent, n, j, rec, ovf, novf);
 }
+
+/* number of rows too long for an inline record */
+__global__ void k_win_count_long(int n, const i64 *__restrict__ Ap, int limit, int *count)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && Ap[i + 1] - Ap[i] > limit)
+		atomicAdd(count, 1);
+}
+
+/* marks the columns of one adjacency record (and of its overflow record); NEW(c) is what happens to a column seen for
+ * the first time */
+#define WIN_EXPAND(ADJ, NEWCOL)                                                              \
+	_Pragma("unroll") for (int k_ = 0; k_ < K; k_++) {                                       \
+		const int c_ = (ADJ)[k_];                                                            \
+		if (c_ >= 0) {                                                                       \
+			my_edges += 1;                                                                   \
+			const unsigned bit_ = 1u << (c_ & 31);                                           \
+			if (!(atomicOr(&vis[c_ >> 5], bit_) & bit_)) { NEWCOL(c_) }                      \
+		} else if (c_ <= -16) {                                                              \
+			const int *o_ = a.ovf + (size_t) (-c_ - 16) * WIN_OVF;                           \
+			for (int q_ = 0; q_ < WIN_OVF; q_++) {                                           \
+				const int d_ = o_[q_];                                                       \
+				if (d_ < 0)                                                                  \
+					break;                                                                   \
+				my_edges += 1;                                                               \
+				const unsigned bit_ = 1u << (d_ & 31);                                       \
+				if (!(atomicOr(&vis[d_ >> 5], bit_) & bit_)) { NEWCOL(d_) }                  \
+			}                                                                                \
+		}                                                                                    \
+	}
 
 /* rows that are not pivotal and hold an entry on a non-pivotal column */
 __global__ void k_win_flag_rows(int n, const i64 *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ pinv,
@@ -317,20 +378,8 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 						}
 						if (adj[0] != -2) {
 							my_edges += 1;
-#pragma unroll
-							for (int k = 0; k < K; k++) {
-								const int c = adj[k];
-								if (c < 0)
-									continue;
-								my_edges += 1;
-								const unsigned bit = 1u << (c & 31);
-								const unsigned old = atomicOr(&vis[c >> 5], bit);
-								if (!(old & bit)) {
-									const int at = atomicAdd(&s_tail, 1);
-									ring[at & (WIN_RING - 1)] = c;
-									queue[at] = c;
-								}
-							}
+#define WIN_PUSH(c) { const int at_ = atomicAdd(&s_tail, 1); ring[at_ & (WIN_RING - 1)] = (c); queue[at_] = (c); }
+							WIN_EXPAND(adj, WIN_PUSH)
 						}
 					}
 					__syncwarp();
@@ -393,24 +442,8 @@ __global__ void __launch_bounds__(WIN_BFS_THREADS) k_win_bfs(WinArgs a)
 					if (adj[u][0] == -2)
 						continue;
 					my_edges += 1;
-#pragma unroll
-					for (int k = 0; k < K; k++) {
-						const int c = adj[u][k];
-						if (c < 0)
-							continue;
-						my_edges += 1;
-						const unsigned bit = 1u << (c & 31);
-						const unsigned old = atomicOr(&vis[c >> 5], bit);
-						if (!(old & bit)) {
-							if (js[u] < 0 && !last) {
-								js[u] = c;                  /* kept: expanded by this thread in the next round */
-							} else {
-								const int at = atomicAdd(&s_tail, 1);
-								ring[at & (WIN_RING - 1)] = c;
-								queue[at] = c;
-							}
-						}
-					}
+#define WIN_KEEP_OR_PUSH(c) { if (js[u] < 0 && !last) js[u] = (c); else WIN_PUSH(c) }
+					WIN_EXPAND(adj[u], WIN_KEEP_OR_PUSH)
 				}
 			}
 		}
@@ -621,14 +654,7 @@ __global__ void __launch_bounds__(32 * W) k_win_resolve(WinArgs a)
 		a.pinv[row] = c0;
 		int ent[WIN_MAXC];
 		load_row16(a.lrow, a.slotlidx[tid], ent);
-		int cnt = 0;
-		int *rec = a.padj + (size_t) c0 * K;
-#pragma unroll
-		for (int k = 0; k < WIN_MAXC; k++)
-			if (ent[k] >= 0 && ent[k] != c0 && cnt < K)
-				rec[cnt++] = ent[k];
-		for (; cnt < K; cnt++)
-			rec[cnt] = -1;
+		win_build_record<K>(ent, WIN_MAXC, c0, a.padj + (size_t) c0 * K, a.ovf, a.novf);
 		atomicAdd(a.found, 1);
 	}
 }
@@ -658,7 +684,7 @@ static void run_windows(WinArgs &a, size_t bfs_smem, size_t res_smem, int max_wi
 	cudaStream_t s = ctx().stream;
 	CUDA_CHECK(cudaFuncSetAttribute(k_win_bfs<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bfs_smem));
 	CUDA_CHECK(cudaFuncSetAttribute(k_win_resolve<K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) res_smem));
-	k_win_padj_init<K><<<cdiv(a.m, 256), 256, 0, s>>>(a.m, a.Ap, a.Aj, a.qinv, a.padj);
+	k_win_padj_init<K><<<cdiv(a.m, 256), 256, 0, s>>>(a.m, a.Ap, a.Aj, a.qinv, a.padj, a.ovf, a.novf);
 	LAUNCHED(1);
 	int done = 0;
 	while (done < max_windows) {
@@ -697,7 +723,7 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	Wn = Wn >= 1024 ? 1024 : (Wn >= 512 ? 512 : 256);
 	a.Wn = Wn;
 	a.W = Wn / 32;
-	a.K = longest_row <= 5 ? 4 : (longest_row <= 9 ? 8 : 16);
+	a.K = longest_row <= 5 ? 4 : 8;      /* longer rows (up to WIN_MAXC entries) spill into an overflow record */
 	a.Ap = A.p;
 	a.Aj = A.j;
 	a.qinv = d_qinv;
@@ -733,6 +759,15 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	a.list = list.ptr;
 	a.lrow = lrow.ptr;
 	a.queue_cap = m + WIN_MAXC;
+	/* overflow records: one per row that does not fit an inline record (a row becomes a pivot row at most once) */
+	DevBuf<int> nlong(2);
+	nlong.zero(s);
+	k_win_count_long<<<cdiv(n, 256), 256, 0, s>>>(n, A.p, a.K + 1, nlong.ptr);
+	LAUNCHED(1);
+	const int novf_cap = fetch(nlong.ptr);
+	DevBuf<int> ovf((size_t) std::max(novf_cap, 1) * WIN_OVF);
+	a.ovf = ovf.ptr;
+	a.novf = nlong.ptr + 1;
 	DevBuf<int> padj((size_t) m * a.K), counters(4), slotrow((size_t) Wn), slotlidx((size_t) Wn), slotnc((size_t) Wn),
 	    slotcol((size_t) Wn * WIN_MAXC), slotvec((size_t) Wn * WIN_MAXC), tent((size_t) Wn), colmark((size_t) m),
 	    replist((size_t) Wn * WIN_MAXC), queues((size_t) Wn * a.queue_cap);
@@ -769,10 +804,8 @@ bool greedy_windowed(const DevCsr &A, int *d_pinv, int *d_qinv, i64 longest_row,
 	} while (0)
 	if (a.K == 4)
 		WIN_DISPATCH(4);
-	else if (a.K == 8)
-		WIN_DISPATCH(8);
 	else
-		WIN_DISPATCH(16);
+		WIN_DISPATCH(8);
 	return true;
 }
 
