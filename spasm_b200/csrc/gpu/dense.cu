@@ -601,7 +601,9 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 	static cudaStream_t s2 = nullptr;
 	static cudaEvent_t ev_m[2] = {nullptr, nullptr}, ev_g2[2] = {nullptr, nullptr};
 	if (!s2) {
-		CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+		int prio_least = 0, prio_greatest = 0;
+		CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+		CUDA_CHECK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_least));      /* the main stream has the highest */
 		for (int k = 0; k < 2; k++) {
 			CUDA_CHECK(cudaEventCreateWithFlags(&ev_m[k], cudaEventDisableTiming));
 			CUDA_CHECK(cudaEventCreateWithFlags(&ev_g2[k], cudaEventDisableTiming));

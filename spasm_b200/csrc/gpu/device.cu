@@ -58,7 +58,11 @@ Context &ctx()
 	g_ctx.sm_count = prop.multiProcessorCount;
 	g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
 	g_ctx.verbose = g_verbose;
-	CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+	/* the library's stream has the highest priority: the dense echelon runs its wide trailing updates on a second,
+	 * lowest-priority stream, and the panel factorisation queued behind them on this one must get the SMs they free */
+	int prio_least = 0, prio_greatest = 0;
+	CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+	CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.stream, cudaStreamNonBlocking, prio_greatest));
 	/* a memory pool OWNED by the library (the device's default pool is shared with every other cudaMallocAsync user of
 	 * the process and is left alone): freed blocks stay in it instead of going back to the driver at every
 	 * synchronisation; spasm_b200_trim() gives everything back */

@@ -855,6 +855,7 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			queues.alloc((size_t) blocks * a.queue_cap);
 			bitmaps.alloc(a.use_smem ? 1 : (size_t) blocks * 2 * a.words);
 			status.zero(s);
+			journal.zero(s);       /* every slot is written before it is published; zeroed so that initcheck sees it that way too */
 		};
 		/* development: run the ordered kernel as well, from the same starting point, and report the differences */
 		static const bool shadow = getenv("SPASM_B200_GREEDY_SHADOW") != NULL;
@@ -893,6 +894,7 @@ PivotCounts pivots_find(const DevCsr &A, int *d_pinv, int *d_qinv, bool greedy)
 			o.n = n; o.m = m; o.words = a.words; o.queue_cap = a.queue_cap; o.use_smem = a.use_smem;
 			o.Ap = A.p; o.Aj = A.j; o.qinv = d_qinv; o.pinv = d_pinv;
 			DevBuf<int> surv((size_t) n * SURV_SLOTS);
+			surv.fill_byte(0xff, s);
 			o.journal = journal.ptr;
 			o.npiv = counters.ptr + 3;
 			o.reserved = counters.ptr + 4;
