@@ -769,7 +769,7 @@ k_panel_solve_flow(const i64 *__restrict__ ptr, const int *__restrict__ src, con
  *     double-buffered so the prefetch of d's dependents does not overwrite what the publication of c still reads).
  * When no dependent is certain the CTA publishes at once and continues with a dependent its decrements released
  * (as before), or polls the queue.  Each column is still written once, from final columns: same values.
- * Needs one right-hand-side group per compute thread (R4 <= blockDim.x - 64); wider batches take the first version.
+ * Needs at most FLOW2_G right-hand-side groups per compute thread (R4 <= 2 (blockDim.x - 64)); wider batches take the first version.
  */
 struct FlowMeta2 {             /* 24 ints = 96 bytes: one dependent of a column in the per-column blob (see k_flow2_blob) */
 	int node, cnt, ready, pad;
@@ -779,6 +779,7 @@ struct FlowMeta2 {             /* 24 ints = 96 bytes: one dependent of a column 
 };
 static_assert(sizeof(FlowMeta2) == 88 + 8 || sizeof(FlowMeta2) == 104, "FlowMeta2 layout");
 #define FLOW2_WORDS ((int) (sizeof(FlowMeta2) / sizeof(int)))
+#define FLOW2_G 2               /* groups of four right-hand sides per compute thread: batches of up to 7680 */
 
 /* blob[c] = the FlowMeta2 records of the first FLOW_MAXD dependents of column c (their dependency lists and their own
  * ranges of dependents), contiguous: the prefetch of a hop is ONE coalesced copy instead of a chain of four dependent
@@ -860,7 +861,10 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 	int buf = 0;
 	bool have_cur = false;
 	int fwd_col = -1;
-	int4 fwd = make_int4(0, 0, 0, 0);
+	int4 fwd[FLOW2_G];
+#pragma unroll
+	for (int g = 0; g < FLOW2_G; g++)
+		fwd[g] = make_int4(0, 0, 0, 0);
 	if (tid == 0)
 		pub.valid = 0;
 	__syncthreads();
@@ -926,9 +930,13 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 		const int c = cur.node;
 		const i64 rb = cur.rb, re = cur.re;
 		if (tid < T3) {
-			/* ---- 2a. the column, one group of four right-hand sides per thread */
-			if (tid < R4) {
-				const int r = tid;
+			/* ---- 2a. the column: up to FLOW2_G groups of four right-hand sides per thread, each kept in a register for
+			 * the next hop */
+#pragma unroll
+			for (int g = 0; g < FLOW2_G; g++) {
+				const int r = tid + g * T3;
+				if (r >= R4)
+					break;
 				const int cnt = cur.cnt, cached = min(cnt, FLOW_MAXE);
 				const i64 e0 = cur.e0;
 				int4 *Xc = X + (size_t) c * ld4;
@@ -943,7 +951,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 					for (int u = 0; u < 4; u++) {
 						const int sc = (e + u < cached) ? cur.src[e + u] : src[e0 + e + u];
 						v[u] = (e + u < cached) ? cur.val[e + u] : val[e0 + e + u];
-						xs[u] = (sc == fwd_col) ? fwd : __ldcg(&X[(size_t) sc * ld4 + r]);
+						xs[u] = (sc == fwd_col) ? fwd[g] : __ldcg(&X[(size_t) sc * ld4 + r]);
 					}
 					if (pendingred + 4 > F.delay) {
 						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
@@ -961,7 +969,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				for (; e < cnt; e++) {
 					const i64 v = (e < cached) ? cur.val[e] : val[e0 + e];
 					const int sc = (e < cached) ? cur.src[e] : src[e0 + e];
-					const int4 xs = (sc == fwd_col) ? fwd : __ldcg(&X[(size_t) sc * ld4 + r]);
+					const int4 xs = (sc == fwd_col) ? fwd[g] : __ldcg(&X[(size_t) sc * ld4 + r]);
 					if (pendingred + 1 > F.delay) {
 						a0 = zp_reduce(a0, F); a1 = zp_reduce(a1, F); a2 = zp_reduce(a2, F); a3 = zp_reduce(a3, F);
 						pendingred = 0;
@@ -974,7 +982,7 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				}
 				b.x = zp_reduce(a0, F); b.y = zp_reduce(a1, F); b.z = zp_reduce(a2, F); b.w = zp_reduce(a3, F);
 				Xc[r] = b;
-				fwd = b;
+				fwd[g] = b;
 			}
 			fwd_col = c;
 			/* lazy schedule: the level of the column is a by-product of the pass (its dependencies are final) */
@@ -998,6 +1006,19 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 					gdst[w] = gsrc[w];
 			}
 			__syncwarp();
+			/* warm the L2 for the next hop: the right-hand sides and the blob of every dependent (the panel and the blob
+			 * array are far larger than the L2, a cold column costs a DRAM round trip on the critical path) */
+			for (int di = 0; di < FLOW_MAXD; di++) {
+				const int d = dp[di].node;
+				if (d < 0)
+					break;
+				const char *xrow = reinterpret_cast<const char *>(X + (size_t) d * ld4);
+				for (int off = lane * 128; off < R4 * 16; off += 32 * 128)
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + off));
+				const char *brow = reinterpret_cast<const char *>(blob + (size_t) d * FLOW_MAXD);
+				if (lane * 128 < (int) (FLOW_MAXD * sizeof(FlowMeta2)))
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(brow + lane * 128));
+			}
 			for (int pass = 0; pass < (FLOW_MAXD * FLOW_MAXE) / 32; pass++) {
 				const int item = pass * 32 + lane;
 				const int di = item / FLOW_MAXE, ei = item % FLOW_MAXE;
@@ -1260,7 +1281,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 		int threads = getenv("SPASM_B200_FLOW_THREADS") ? atoi(getenv("SPASM_B200_FLOW_THREADS")) : (R4 > 480 ? 1024 : R4 > 224 ? 512 : 256);      /* one warp of the CTA is the prefetcher when the batch fits */
 		threads = std::max(64, std::min(1024, threads & ~31));
 		static const bool flow1 = getenv("SPASM_B200_FLOW1") != NULL;
-		const bool flow2 = !flow1 && R4 <= 1024 - 64;      /* one right-hand-side group per compute thread: register forwarding */
+		const bool flow2 = !flow1 && R4 <= FLOW2_G * (1024 - 64);      /* the groups of a thread stay in registers: register forwarding */
 		GpuTimer tk;
 		if (flow2) {
 			threads = R4 + 64 > 512 ? 1024 : R4 + 64 > 256 ? 512 : 256;
