@@ -830,6 +830,201 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 	}
 }
 
+/* ------------------------------------------------------------------ sparse finisher (GPLU) */
+
+__global__ void k_gplu_mark_cols(i64 nnz, const int *__restrict__ Sj, int *flag)
+{
+	i64 e = (i64) blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < nnz)
+		flag[Sj[e]] = 1;
+}
+
+__global__ void k_gplu_list_cols(int m, const int *__restrict__ flag, const int *__restrict__ off, int *cols, int *colmap)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m)
+		return;
+	colmap[j] = flag[j] ? off[j] : -1;
+	if (flag[j])
+		cols[off[j]] = j;
+}
+
+/* D[r][colmap[j]] = x for every entry (j, x) of row r */
+__global__ void k_gplu_csr_to_dense(int R, const i64 *__restrict__ Sp, const int *__restrict__ Sj, const i32 *__restrict__ Sx,
+                                    const int *__restrict__ colmap, i32 *D, int ld)
+{
+	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= R)
+		return;
+	for (i64 e = Sp[warp] + lane; e < Sp[warp + 1]; e += 32)
+		D[(size_t) warp * ld + colmap[Sj[e]]] = Sx[e];
+}
+
+__global__ void k_gplu_register(int nnew, const i64 *__restrict__ Rp, const int *__restrict__ Rj, int un0, int *Uqinv)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < nnew)
+		Uqinv[Rj[Rp[t]]] = un0 + t;
+}
+
+/* append nnew rows (device CSR, pivot first and equal to 1) to the structural U */
+static void append_device_rows(Engine &E, DevBuf<i64> &Rp, DevBuf<int> &Rj, DevBuf<i32> &Rx, int nnew, i64 nnz)
+{
+	cudaStream_t s = ctx().stream;
+	DevCsr &U = E.U;
+	const int un0 = U.n;
+	const i64 unz0 = U.nnz;
+	DevBuf<i64> np((size_t) un0 + nnew + 1);
+	DevBuf<int> nj((size_t) std::max<i64>(unz0 + nnz, 1));
+	DevBuf<i32> nx((size_t) std::max<i64>(unz0 + nnz, 1));
+	if (un0 > 0) {
+		CUDA_CHECK(cudaMemcpyAsync(np.ptr, U.p.ptr, ((size_t) un0 + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(nj.ptr, U.j.ptr, (size_t) unz0 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		CUDA_CHECK(cudaMemcpyAsync(nx.ptr, U.x.ptr, (size_t) unz0 * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+	} else {
+		CUDA_CHECK(cudaMemsetAsync(np.ptr, 0, sizeof(i64), s));
+	}
+	k_gplu_register<<<cdiv(nnew, 256), 256, 0, s>>>(nnew, Rp.ptr, Rj.ptr, un0, E.Uqinv.ptr);
+	if (unz0)
+		k_add_offset<<<cdiv(nnew + 1, 256), 256, 0, s>>>(Rp.ptr, nnew + 1, unz0);
+	LAUNCHED(2);
+	CUDA_CHECK(cudaMemcpyAsync(np.ptr + un0, Rp.ptr, ((size_t) nnew + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s));
+	CUDA_CHECK(cudaMemcpyAsync(nj.ptr + unz0, Rj.ptr, (size_t) nnz * sizeof(int), cudaMemcpyDeviceToDevice, s));
+	CUDA_CHECK(cudaMemcpyAsync(nx.ptr + unz0, Rx.ptr, (size_t) nnz * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+	sync();
+	U.p = std::move(np);
+	U.j = std::move(nj);
+	U.x = std::move(nx);
+	U.n = un0 + nnew;
+	U.nnz = unz0 + nnz;
+	E.G_ready = false;                 /* the solve schedule is rebuilt before the next batch */
+}
+
+/* reference: src/spasm_echelonize.c:30-51, against a U that is entirely sparse: ceil(128 / log2 p) random combinations of
+ * all the rows must reduce to zero */
+static bool test_completion_sparse(Engine &E, const DevCsr &A, const int *p, int n)
+{
+	if (n == 0 || A.nnz == 0)
+		return true;
+	cudaStream_t s = ctx().stream;
+	const int Sn = (int) ceil(128 / log2((double) E.prime));
+	LOG("[echelonize/completion] Testing completion with %d random linear combinations (rank %d)\n", Sn, E.rank());
+	std::vector<int> rows((size_t) Sn * n);
+	std::vector<i32> coef((size_t) Sn * n);
+	for (int k = 0; k < Sn; k++) {
+		spasm_prng_ctx prng;
+		spasm_prng_seed_simple(E.prime, (u64) k, 0, &prng);
+		for (int i = 0; i < n; i++) {
+			rows[(size_t) k * n + i] = p[i];
+			coef[(size_t) k * n + i] = spasm_prng_ZZp(&prng);
+		}
+	}
+	DevBuf<int> d_rows;
+	DevBuf<i32> d_coef;
+	d_rows.upload(rows.data(), rows.size(), s);
+	d_coef.upload(coef.data(), coef.size(), s);
+	E.solve_combos(A, d_rows.ptr, d_coef.ptr, Sn, n);
+	const i64 left = panel_count_nonzero(E.panel, E.Uqinv.ptr);
+	record_block(Sn, E.m - E.rank(), left == 0 ? 0 : 1, 0);
+	return left == 0;
+}
+
+/*
+ * The reference's sparse finisher (echelonize_GPLU, src/spasm_echelonize.c:54-187) processes the rows one at a time:
+ * solve against the current U, leftmost entry on a non-pivotal column = new pivot, append the scaled row to U (which
+ * stays SPARSE), early abort when the rank is reached or when no pivot was found for a while and random combinations of
+ * the rows all reduce to zero.  Here the rows are processed in batches: one batched solve against the current U, the
+ * reduced rows (sparse, on non-pivotal columns) are compacted to the columns they touch and echelonized among
+ * themselves (dense_rref on a batch x touched-columns block), the resulting rows go back to U as sparse rows.  The pivot
+ * columns are the leading positions of the row space either way (an invariant of the row space), so rank, pivot columns,
+ * RREF and kernel are the reference's; U never holds a dense row over all remaining columns (the dense block
+ * path needs rank x Sm x 4 bytes).  Chosen when the Schur complement is sparse (density <= sparsity_threshold).
+ */
+static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+{
+	(void) opts;
+	cudaStream_t s = ctx().stream;
+	const int m = E.m;
+	const int r_ub = spasm_min(A.n, m);
+	const int batch = getenv("SPASM_B200_GPLU_BATCH") ? std::max(1, atoi(getenv("SPASM_B200_GPLU_BATCH"))) : 1024;
+	LOG("[echelonize/GPLU] processing matrix of dimension %d x %d\n", n, m);
+	int rows_since_last_pivot = 0;
+	bool early_abort_done = false;
+	DevBuf<int> flag((size_t) m + 1), off((size_t) m + 1), cols((size_t) m), colmap((size_t) m);
+	static DevBuf<char> tmp;
+	for (int done = 0; done < n;) {
+		if (E.U.n >= r_ub) {
+			LOG("\n[echelonize/GPLU] full rank reached\n");
+			break;
+		}
+		if (!early_abort_done && rows_since_last_pivot > 10 && rows_since_last_pivot > n / 100) {
+			LOG("\n[echelonize/GPLU] testing for early abort...\n");
+			if (test_completion_sparse(E, A, p, n))
+				break;
+			early_abort_done = true;
+		}
+		const int R = std::min(batch, n - done);
+		DevBuf<int> d_rows;
+		d_rows.upload(p + done, (size_t) R, s);
+		E.solve_rows(A, d_rows.ptr, R, false);
+		done += R;
+		DevBuf<i64> Sp;
+		DevBuf<int> Sj;
+		DevBuf<i32> Sx;
+		i64 nnz = 0;
+		panel_to_csr(E.panel, E.Uqinv.ptr, nullptr, 0, nullptr, Sp, Sj, Sx, nnz);
+		if (nnz == 0) {
+			rows_since_last_pivot += R;
+			continue;
+		}
+		/* the columns the batch touches */
+		flag.zero(s);
+		k_gplu_mark_cols<<<cdiv((size_t) nnz, 256), 256, 0, s>>>(nnz, Sj.ptr, flag.ptr);
+		size_t bytes = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.ptr, off.ptr, m + 1, s);
+		tmp.ensure(bytes + 16);
+		cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, flag.ptr, off.ptr, m + 1, s);
+		k_gplu_list_cols<<<cdiv(m, 256), 256, 0, s>>>(m, flag.ptr, off.ptr, cols.ptr, colmap.ptr);
+		LAUNCHED(3);
+		const int C = fetch(off.ptr + m);
+		const int ld = std::max((C + 3) & ~3, 4);
+		DevBuf<i32> D((size_t) R * ld);
+		D.zero(s);
+		k_gplu_csr_to_dense<<<cdiv((size_t) R * 32, 256), 256, 0, s>>>(R, Sp.ptr, Sj.ptr, Sx.ptr, colmap.ptr, D.ptr, ld);
+		LAUNCHED(1);
+		GpuTimer t;
+		t.start();
+		RrefResult res = dense_rref(D.ptr, R, C, ld, E.F);
+		stats().pub.ms_dense += t.stop_ms();
+		record_block(R, C, res.rank, -2);
+		if (res.rank == 0) {
+			rows_since_last_pivot += R;
+			continue;
+		}
+		/* the pivot rows of the block, as sparse rows of U (pivot first) */
+		DevBuf<int> d_prow, d_pcol;
+		d_prow.upload(res.pivrow.data(), res.pivrow.size(), s);
+		d_pcol.upload(res.pivcol.data(), res.pivcol.size(), s);
+		DevBuf<i32> Dr((size_t) res.rank * ld);
+		dense_gather_rows(D.ptr, ld, d_prow.ptr, res.rank, C, Dr.ptr, ld);
+		std::vector<unsigned char> own((size_t) std::max(C, 1), 0);
+		for (int c : res.pivcol)
+			own[c] = 1;
+		DevBuf<unsigned char> d_own;
+		d_own.upload(own.data(), own.size(), s);
+		DevBuf<i64> Rp;
+		DevBuf<int> Rj;
+		DevBuf<i32> Rx;
+		i64 rnz = 0;
+		dense_rows_to_csr(Dr.ptr, ld, res.rank, C, d_pcol.ptr, d_own.ptr, cols.ptr, Rp, Rj, Rx, rnz);
+		append_device_rows(E, Rp, Rj, Rx, res.rank, rnz);
+		rows_since_last_pivot = 0;
+		early_abort_done = false;
+		LOG("\r[echelonize/GPLU] %d / %d [|U| = %" PRId64 "] --- rank >= %d", done, n, E.U.nnz, E.U.n);
+	}
+	LOG("\n");
+}
+
 /* ------------------------------------------------------------------ result assembly */
 
 /* copy the echelon form to malloc'ed host memory: structural rows, then the dense rows in the
@@ -1055,6 +1250,12 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			 * is the same; here it is computed block-wise on the GPU.  (a sequential GPU GPLU
 			 * is a later row.)  No low-rank switch: GPLU processes every row. */
 			st.pub.finish = 3;
+			static const bool gplu_dense = getenv("SPASM_B200_GPLU_DENSE") != NULL;
+			if (!gplu_dense && comm_world() == 1) {
+				finish_gplu(E, *cur, p.data() + npiv, n - npiv, opts);
+				lap("finish");
+				return;
+			}
 			{
 				/* the block path keeps every new pivot row as a dense row over the columns that are non-pivotal now:
 				 * rank_ub x Sm x 4 bytes (+ the packed copy).  The reference keeps U sparse here.  Refuse early, with

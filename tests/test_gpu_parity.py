@@ -211,3 +211,19 @@ def test_reference_tools_relinked_against_the_library(tmp_path):
                     rows.setdefault(int(p[0]), []).append((int(p[1]), int(p[2])))
             return n, m, sorted((v[0], tuple(sorted(v[1:]))) for v in rows.values())
         assert canon(a.stdout) == canon(b.stdout)
+
+
+@pytest.mark.parametrize("batch", ["7", "64", "1024"])
+def test_sparse_gplu_finisher_in_small_batches(product, monkeypatch, batch):
+    """The sparse finisher (reference: echelonize_GPLU, src/spasm_echelonize.c:54-187) processes the leftover rows in
+    batches and appends the new pivots to U as SPARSE rows; whatever the batch size the canonical result is the
+    reference's.  Small batches also exercise the early-abort test (no pivot for a while -> random combinations of all
+    the rows must vanish, :90-95) on the rank-deficient planted matrix."""
+    monkeypatch.setenv("SPASM_B200_GPLU_BATCH", batch)
+    opts = dict(enable_dense=False, enable_tall_and_skinny=False)
+    for t in (synthetic.config4(0.01), synthetic.config1(0.03), synthetic.config2(0.01).transposed()):
+        got = util.run_product(product, t, **opts)
+        want = util.run_oracle(t, **opts)
+        assert got["finish"] == 3 == want["finish"]
+        util.assert_same(got, want, keys=("rank", "pivot_columns", "rref", "kernel", "kernel_dim", "found"), what=f"GPLU batch {batch}")
+        util.check_echelon_form(got["_U"], got["_qinv"])
