@@ -506,7 +506,7 @@ def main() -> None:
                 leg["speedup_vs_single_gpu"] = single["total"] / legN["total"]
                 leg["rref_speedup_vs_single_gpu"] = single["rref"] / legN["rref"]
             lines[0]["scale_leg"] = leg
-        if not args.no_schur_leg and args.workload in ("config2", "all"):
+        if not args.no_schur_leg and world == 1 and args.workload in ("config2", "all"):
             try:
                 rows, nnz, sec = schur_leg(L, host)
                 sch = {"workload": "config1 (20000x20000): spasm_schur forced on the round-0 non-pivotal rows (SURVEY 8d)", "rows": rows, "nnz_out": nnz,
