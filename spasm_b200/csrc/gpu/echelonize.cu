@@ -953,7 +953,7 @@ static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const s
 	DevBuf<int> flag((size_t) m + 1), off((size_t) m + 1), cols((size_t) m), colmap((size_t) m);
 	static DevBuf<char> tmp;
 	for (int done = 0; done < n;) {
-		if (E.U.n >= r_ub) {
+		if (E.U.n == r_ub) {               /* the reference's test, literally (:88): A is the CURRENT matrix, U->n the total rank */
 			LOG("\n[echelonize/GPLU] full rank reached\n");
 			break;
 		}
