@@ -447,7 +447,7 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 	std::vector<int> pivcol((size_t) std::max(n, 1));
 	for (int i = 0; i < n; i++)
 		pivcol[i] = U->j[U->p[i]];
-	const int cap = panel_capacity(m, 64.0);
+	const int cap = panel_capacity(m, 16.0);
 	std::vector<HostPiece> pieces;
 	/* several ranks: each one reduces a contiguous slice of the rows (they are independent given U, rref.c:44-56) */
 	int chunk, slice_begin, slice_end;
@@ -514,7 +514,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact)
 	for (int j = 0; j < m; j++)
 		if (qinv[j] < 0)
 			freecols.push_back(j);
-	const int cap = panel_capacity(std::max(n, 1), 64.0);
+	const int cap = panel_capacity(std::max(n, 1), 16.0);
 	std::vector<HostPiece> pieces;
 	std::vector<int> colslot((size_t) std::max(m, 1));
 	Panel P;
