@@ -97,7 +97,7 @@ static struct spasm_csr *pieces_to_host(const std::vector<HostPiece> &pieces, in
  * order (= row order of the result), in HBM.  One all-gather of the piece sizes, then one NCCL group of broadcasts,
  * each piece from its owner (variable lengths, no padding).
  */
-#define MAX_PIECES_PER_RANK 255
+#define MAX_PIECES_PER_RANK 4095
 static void exchange_pieces(std::vector<HostPiece> &pieces)
 {
 	const int world = comm_world(), me = comm_rank();
