@@ -812,6 +812,21 @@ __global__ void k_flow2_blob(int n, const i64 *__restrict__ ptr, const int *__re
 		}
 	}
 	blob[(size_t) c * FLOW_MAXD + di] = m;
+	if (di == 0) {
+		/* the column's OWN record (what a CTA needs when it takes the column from the queue), after the dependents' blobs */
+		FlowMeta2 o;
+		o.node = c; o.ready = 0; o.pad = 0;
+		o.e0 = ptr[c];
+		o.cnt = (int) (ptr[c + 1] - o.e0);
+		o.rb = rb;
+		o.re = re;
+#pragma unroll
+		for (int e = 0; e < FLOW_MAXE; e++) {
+			o.src[e] = (e < o.cnt) ? src[o.e0 + e] : -1;
+			o.val[e] = (e < o.cnt) ? val[o.e0 + e] : 0;
+		}
+		blob[(size_t) n * FLOW_MAXD + c] = o;
+	}
 }
 
 struct FlowPub {
@@ -848,7 +863,7 @@ __global__ void __launch_bounds__(1024)
 k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                     const i64 *__restrict__ rptr, const int *__restrict__ rdst,
                     int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
-                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob)
+                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob, int nnodes)
 {
 	__shared__ int s_node, s_next, s_capt;
 	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
@@ -911,18 +926,12 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 				return;
 			}
 			n_polled++;
-			const i64 e0 = ptr[c0];
-			const int cnt = (int) (ptr[c0 + 1] - e0);
-			if (tid < FLOW_MAXE && tid < cnt) {
-				cur.src[tid] = src[e0 + tid];
-				cur.val[tid] = val[e0 + tid];
-			}
-			if (tid == 0) {
-				cur.node = c0;
-				cur.cnt = cnt;
-				cur.e0 = e0;
-				cur.rb = rptr[c0];
-				cur.re = rptr[c0 + 1];
+			{
+				/* one coalesced load of the column's own record instead of ptr -> src/val -> rptr */
+				const int *gsrc = reinterpret_cast<const int *>(blob + (size_t) nnodes * FLOW_MAXD + c0);
+				int *gdst = reinterpret_cast<int *>(&cur);
+				if (tid < FLOW2_WORDS)
+					gdst[tid] = gsrc[tid];
 			}
 			fwd_col = -1;
 		}
@@ -1289,7 +1298,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			static const bool hoptrace = getenv("SPASM_B200_TRACE") != NULL;
 			DevBuf<unsigned long long> hopstats(3);
 			hopstats.zero(s);
-			DevBuf<char> blob((size_t) n * FLOW_MAXD * sizeof(FlowMeta2));
+			DevBuf<char> blob(((size_t) n * FLOW_MAXD + (size_t) n) * sizeof(FlowMeta2));
 			k_flow2_blob<<<cdiv((size_t) n * FLOW_MAXD, 256), 256, 0, s>>>(n, G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, (FlowMeta2 *) blob.ptr);
 			LAUNCHED(1);
 			k_flow2_flags<<<cdiv(n, 256), 256, 0, s>>>(n, G.ptr.ptr, doneflag.ptr);
@@ -1300,7 +1309,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			k_panel_solve_flow2<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
 			                                          G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3, doneflag.ptr,
 			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr, hoptrace ? hopstats.ptr : nullptr,
-			                                          (const FlowMeta2 *) blob.ptr);
+			                                          (const FlowMeta2 *) blob.ptr, n);
 			LAUNCHED(2);
 			KERNEL_CHECK();
 			stats().pub.ms_k_panel_solve += tk.stop_ms();      /* before doneflag goes out of scope: the stop synchronises */
