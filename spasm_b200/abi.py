@@ -45,6 +45,10 @@ class EchelonizeOpts(C.Structure):  # include/spasm.h: struct echelonize_opts
                 ("low_rank_start_weight", C.c_double)]
 
 
+class RankCertificate(C.Structure):   # include/spasm.h: struct spasm_rank_certificate
+    _fields_ = [("r", C.c_int), ("prime", i64), ("hash", C.c_uint8 * 32), ("i", c_int_p), ("j", c_int_p), ("x", i32_p), ("y", i32_p)]
+
+
 class Sha256Ctx(C.Structure):
     _fields_ = [("h", C.c_uint32 * 8), ("Nl", C.c_uint32), ("Nh", C.c_uint32), ("data", C.c_uint32 * 16),
                 ("num", C.c_uint32), ("md_len", C.c_uint32)]
@@ -61,6 +65,7 @@ CsrP = C.POINTER(Csr)
 TripletP = C.POINTER(Triplet)
 LuP = C.POINTER(Lu)
 OptsP = C.POINTER(EchelonizeOpts)
+CertP = C.POINTER(RankCertificate)
 
 # name -> (restype, argtypes); every symbol include/spasm.h declares
 PROTOTYPES = {
@@ -140,10 +145,10 @@ PROTOTYPES = {
     "spasm_kernel": (CsrP, [LuP]),
     "spasm_solve": (C.c_bool, [LuP, i32_p, i32_p]),
     "spasm_gesv": (CsrP, [LuP, CsrP, C.POINTER(C.c_bool)]),
-    "spasm_certificate_rank_create": (C.c_void_p, [CsrP, C.c_void_p, LuP]),
-    "spasm_certificate_rank_verify": (C.c_bool, [CsrP, C.c_void_p, C.c_void_p]),
-    "spasm_rank_certificate_save": (None, [C.c_void_p, C.c_void_p]),
-    "spasm_rank_certificate_load": (C.c_bool, [C.c_void_p, C.c_void_p]),
+    "spasm_certificate_rank_create": (CertP, [CsrP, C.c_void_p, LuP]),
+    "spasm_certificate_rank_verify": (C.c_bool, [CsrP, C.c_void_p, CertP]),
+    "spasm_rank_certificate_save": (None, [CertP, C.c_void_p]),
+    "spasm_rank_certificate_load": (C.c_bool, [C.c_void_p, CertP]),
     "spasm_factorization_verify": (C.c_bool, [CsrP, LuP, C.c_uint64]),
 }
 

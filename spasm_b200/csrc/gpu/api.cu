@@ -4,13 +4,15 @@
  * spasm_echelonize, and hand back malloc'ed host results.
  */
 #include <math.h>
+#include <functional>
 #include "engine.cuh"
+#include "lu.cuh"
 #include "stats.cuh"
 
 namespace sb {
 int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool greedy, int round, bool allow_lazy);
 double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R);
-void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S);
+void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S, const std::function<void(int, int)> &after_batch);
 
 #define LOG(...) do { if (ctx().verbose) { fprintf(stderr, __VA_ARGS__); fflush(stderr); } } while (0)
 
@@ -187,6 +189,48 @@ static void append_L_from_panel(Engine &E, struct spasm_triplet *L, const int *r
 			spasm_add_entry(L, row_out[r], hj[e], hx[e]);
 }
 
+/*
+ * L of the factorization, read out of the final echelon form (lu.cu explains why this is THE L of the reference's
+ * definition: the rows of U are independent, so A[i] = sum_k L[i][k] U[k] has one solution).  Row i of L = the
+ * elimination coefficients the batched solve of x * U = A[i] leaves on the pivotal columns; what it leaves on the
+ * other columns must be zero (U spans the rows of A), which is checked.  Rows: all of them when `complete`, the
+ * pivotal ones (fact->p) otherwise -- the reference also keeps the pivotal rows only (echelonize.c:252-270).
+ * reference: src/spasm_echelonize.c:606-614 (L->m = rank, spasm_compress(L), fact->complete).
+ */
+void compute_L(struct spasm_lu *fact, const DevCsr &dA, bool complete)
+{
+	cudaStream_t s = ctx().stream;
+	const int n = dA.n, r = fact->U->n;
+	struct spasm_triplet *L = spasm_triplet_alloc(n, r, std::max<i64>(spasm_nnz(fact->U) + n, 1), dA.prime, true);
+	if (r > 0) {
+		Engine E;
+		engine_from_host(E, fact->U, fact->qinv);
+		std::vector<int> rows;
+		if (complete) {
+			rows.resize((size_t) n);
+			for (int i = 0; i < n; i++)
+				rows[i] = i;
+		} else {
+			rows.assign(fact->p, fact->p + r);
+		}
+		const int cap = panel_capacity(E.m);
+		for (size_t done = 0; done < rows.size(); done += cap) {
+			const int R = (int) std::min<size_t>(cap, rows.size() - done);
+			DevBuf<int> d_rows;
+			d_rows.upload(rows.data() + done, (size_t) R, s);
+			E.solve_rows(dA, d_rows.ptr, R, false);
+			if (panel_count_nonzero(E.panel, E.Uqinv.ptr) != 0)
+				errx(1, "[spasm-b200] internal: a row of the input is not in the span of the echelon form (L mode)");
+			append_L_from_panel(E, L, rows.data() + done, R);
+		}
+	}
+	LOG("[echelonize] L : %" PRId64 " entries\n", L->nz);
+	fact->L = spasm_compress(L);
+	spasm_triplet_free(L);
+	fact->Ltmp = NULL;
+	fact->complete = complete;
+}
+
 static void store_dense(void *S, spasm_datatype datatype, const std::vector<i32> &host, int rows, int ld, int Sm)
 {
 	for (int r = 0; r < rows; r++)
@@ -274,8 +318,6 @@ double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int
 struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, const struct spasm_lu *fact,
                               double est_density, struct spasm_triplet *L, const int *p_in, int *p_out)
 {
-	if (L != NULL)
-		errx(1, "[spasm-b200] spasm_schur: the L path is not part of the B200 build");
 	ctx();
 	Engine E;
 	engine_from_host(E, fact->U, fact->qinv);
@@ -284,7 +326,15 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
 	if (est_density < 0)
 		est_density = estimate_density(E, dA, p, n, 100);     /* keeps the reference's rand() consumption */
 	DevCsr S;
-	schur_sparse(E, dA, p, n, S);
+	std::function<void(int, int)> keep_L;
+	if (L != NULL)
+		keep_L = [&](int done, int R) {
+			std::vector<int> row_out((size_t) R);
+			for (int r = 0; r < R; r++)
+				row_out[r] = (p_in != NULL) ? p_in[p[done + r]] : p[done + r];
+			append_L_from_panel(E, L, row_out.data(), R);
+		};
+	schur_sparse(E, dA, p, n, S, keep_L);
 	if (p_out != NULL)
 		for (int k = 0; k < n; k++)
 			p_out[k] = (p_in != NULL) ? p_in[p[k]] : p[k];
@@ -419,6 +469,78 @@ int spasm_ffpack_rref(i64 prime, int n, int m, void *A, int ldA, spasm_datatype 
 		for (int kk = 0; kk < m; kk++)
 			spasm_datatype_write(A, (size_t) i * ldA + kk, datatype, packed[(size_t) i * m + kk]);
 	return res.rank;
+}
+
+/*
+ * reference: src/spasm_ffpack.cpp:52-75, :88-96 (FFPACK::pPLUQ behind the same signature).  Output layout, as read by
+ * update_fact_after_LU (src/spasm_echelonize.c:276-312) and tests/dense_lu_ffpack.c:88-121: position (i, j) of A is row
+ * p[i], column qinv[j] of the input; j <= min(i, r-1) holds L (its diagonal is not 1), i < r and j > i holds U (unit
+ * diagonal implied).  Computed as in lu.cu: reduced echelon form R (dense.cu) for the pivot columns, C = A[:, pivots],
+ * C = Pi^t Lc Uc, U = Uc * R.  The pivot columns are the column rank profile, in increasing order.
+ */
+int spasm_ffpack_LU(i64 prime, int n, int m, void *A, int ldA, spasm_datatype datatype, size_t *p, size_t *qinv)
+{
+	ctx();
+	cudaStream_t s = ctx().stream;
+	Zp F = make_zp(prime);
+	const int ld = std::max((m + 3) & ~3, 4);
+	std::vector<i32> host((size_t) std::max(n, 1) * ld, 0);
+	spasm_field field;
+	spasm_field_init(prime, field);
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < m; j++)
+			host[(size_t) i * ld + j] = spasm_ZZp_init(field, (i64) spasm_datatype_read(A, (size_t) i * ldA + j, datatype));
+	DevBuf<i32> D, before;
+	D.upload(host.data(), host.size(), s);
+	before.upload(host.data(), host.size(), s);
+	RrefResult res = dense_rref(D.ptr, n, m, ld, F);
+	const int r = res.rank;
+	std::vector<char> is_pivot((size_t) std::max(m, 1), 0);
+	for (int t = 0; t < r; t++) {
+		qinv[t] = res.pivcol[t];
+		is_pivot[res.pivcol[t]] = 1;
+	}
+	int k = r;
+	for (int j = 0; j < m; j++)
+		if (!is_pivot[j])
+			qinv[k++] = j;
+	std::vector<int> lu_row;
+	const int ldc = std::max((r + 3) & ~3, 4);
+	std::vector<i32> hC((size_t) std::max(n, 1) * ldc, 0), hU((size_t) std::max(r, 1) * ld, 0);
+	if (r > 0) {
+		DevBuf<int> d_pc, d_pr;
+		d_pc.upload(res.pivcol.data(), res.pivcol.size(), s);
+		d_pr.upload(res.pivrow.data(), res.pivrow.size(), s);
+		DevBuf<i32> C((size_t) n * ldc), Dr((size_t) r * ld), Ulu((size_t) r * ld);
+		dense_gather_columns(before.ptr, ld, n, d_pc.ptr, r, C.ptr, ldc);
+		dense_lu_fullcol(C.ptr, n, r, ldc, F, lu_row);
+		dense_gather_rows(D.ptr, ld, d_pr.ptr, r, m, Dr.ptr, ld);
+		dense_lu_rows(C.ptr, ldc, r, lu_row, Dr.ptr, ld, m, Ulu.ptr, ld, F);
+		C.download(hC.data(), (size_t) n * ldc, s);
+		Ulu.download(hU.data(), (size_t) r * ld, s);
+		sync();
+	}
+	std::vector<char> used((size_t) std::max(n, 1), 0);
+	for (int t = 0; t < r; t++) {
+		p[t] = lu_row[t];
+		used[lu_row[t]] = 1;
+	}
+	k = r;
+	for (int i = 0; i < n; i++)
+		if (!used[i])
+			p[k++] = i;
+	for (int i = 0; i < n; i++) {
+		const i32 *Lrow = hC.data() + (size_t) p[i] * ldc;
+		for (int j = 0; j < m; j++) {
+			i32 v = 0;
+			if (j < r && j <= i)
+				v = Lrow[j];
+			else if (i < r)
+				v = hU[(size_t) i * ld + qinv[j]];
+			spasm_datatype_write(A, (size_t) i * ldA + j, datatype, v);
+		}
+	}
+	return r;
 }
 
 /* reference: src/spasm_rref.c:22-146 */

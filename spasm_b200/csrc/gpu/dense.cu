@@ -684,9 +684,11 @@ __global__ void k_rows_to_csr(const i32 *__restrict__ D, int ld, int nrows, int 
 			Rx[out] = 1;
 		}
 		i64 written = 1;
+		const int own = pivcol[t];
 		for (int c0 = 0; c0 < width; c0 += 32) {
 			int c = c0 + lane;
-			i32 v = (c < width && !skip[c]) ? row[c] : 0;
+			/* skip == NULL: rows that are not reduced against each other (L mode), only the row's own pivot is implied */
+			i32 v = (c < width && !(skip ? skip[c] : (unsigned char) (c == own))) ? row[c] : 0;
 			unsigned mask = __ballot_sync(0xffffffffu, v != 0);
 			if (EMIT && v != 0) {
 				i64 pos = out + written + __popc(mask & ((1u << lane) - 1));

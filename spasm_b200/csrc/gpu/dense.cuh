@@ -47,7 +47,8 @@ void dense_scatter_rows(const i32 *src, int lds, const int *d_rows, int nrows, c
 
 /* sparse rows (reference: src/spasm_echelonize.c:192-223, update_U_after_rref): for each of the nrows rows of D
  * (ld), the entries on columns c with skip[c] == 0 that are non-zero, as (colmap[c], value), by increasing c,
- * preceded by (colmap[pivcol[t]], 1).  Output CSR arrays on the device. */
+ * preceded by (colmap[pivcol[t]], 1).  d_skip == NULL skips the row's own pivot column only (rows that are not reduced
+ * against each other: the L mode).  Output CSR arrays on the device. */
 void dense_rows_to_csr(const i32 *D, int ld, int nrows, int width, const int *d_pivcol, const unsigned char *d_skip,
                        const int *d_colmap, DevBuf<i64> &Rp, DevBuf<int> &Rj, DevBuf<i32> &Rx, i64 &nnz);
 

@@ -17,8 +17,10 @@
  * the "n -= rr" quirk of the low-rank loop (echelonize.c:369).
  */
 #include <math.h>
+#include <functional>
 #include <cub/cub.cuh>
 #include "engine.cuh"
+#include "lu.cuh"
 #include "stats.cuh"
 
 namespace sb {
@@ -170,6 +172,7 @@ int extract_structural(Engine &E, const DevCsr &A, const int *p_in, int *p, bool
 		p[k++] = i;
 		st.pair_row.push_back(p_in ? p_in[i] : i);
 		st.pair_col.push_back(h_pinv[i]);
+		E.p_struct.push_back(p_in ? p_in[i] : i);      /* fact->p of the L mode: row t of U comes from this row of the input */
 	}
 	for (int i = 0; i < n; i++)
 		if (h_pinv[i] < 0)
@@ -198,7 +201,7 @@ double estimate_density(Engine &E, const DevCsr &A, const int *p, int n, int R)
 
 /* reference: src/spasm_schur.c:61-193.  Rows come out in p order (the reference with one thread) and the entries of
  * a row in the order of the reference's reach pattern (panel.cu: k_schur_emit_dfs). */
-void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
+void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S, const std::function<void(int, int)> &after_batch)
 {
 	cudaStream_t s = ctx().stream;
 	const int cap = panel_capacity(E.m);
@@ -210,6 +213,8 @@ void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
 		DevBuf<int> d_rows;
 		d_rows.upload(p + done, (size_t) R, s);
 		E.solve_rows(A, d_rows.ptr, R, false);
+		if (after_batch)
+			after_batch(done, R);          /* the elimination coefficients are on the pivotal columns of the panel (L, schur.c:164-170) */
 		Piece pc;
 		pc.rows = R;
 		/* count, then emit every row in the order of the reference's DFS pattern (it feeds the next pivot round) */
@@ -244,6 +249,7 @@ void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S)
 }
 
 void prng_combo_coefficients(i64 prime, int N, int w, i32 *d_coef);     /* prng.cu */
+void compute_L(struct spasm_lu *fact, const DevCsr &dA, bool complete);    /* api.cu */
 
 /* ------------------------------------------------------------------ finishing strategies */
 
@@ -775,7 +781,8 @@ static void finish_lowrank(Engine &E, const DevCsr &A, const int *p, int n, cons
 }
 
 /* reference: src/spasm_echelonize.c:385-463 */
-static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts, Speculation *spec = nullptr)
+static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts, Speculation *spec = nullptr,
+                         const int *p_in = nullptr)
 {
 	E.begin_dense();
 	cudaStream_t s = ctx().stream;
@@ -811,7 +818,12 @@ static void finish_dense(Engine &E, const DevCsr &A, const int *p, int n, const 
 			ahead_begin = processed;
 			ahead_end = processed + take;
 		}
-		int rr = E.absorb_block(B.ptr + (size_t) (processed - ahead_begin) * ldB, Sn, ldB);
+		int rr = E.absorb_block(B.ptr + (size_t) (processed - ahead_begin) * ldB, Sn, ldB, E.want_L);
+		if (E.want_L && rr > 0)
+			for (int local : E.blocks.back().lu_row) {       /* update_fact_after_LU, echelonize.c:252-287: Lp[U->n + i] = iorig */
+				const int row = p[local];
+				E.p_dense.push_back(p_in ? p_in[row] : row);
+			}
 		record_block(Sn, Sm, rr, -1);
 		round += 1;
 		processed += Sn;
@@ -940,7 +952,7 @@ static bool test_completion_sparse(Engine &E, const DevCsr &A, const int *p, int
  * RREF and kernel are the reference's; U never holds a dense row over all remaining columns (the dense block
  * path needs rank x Sm x 4 bytes).  Chosen when the Schur complement is sparse (density <= sparsity_threshold).
  */
-static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts)
+static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const struct echelonize_opts *opts, const int *p_in = nullptr)
 {
 	(void) opts;
 	cudaStream_t s = ctx().stream;
@@ -953,11 +965,11 @@ static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const s
 	DevBuf<int> flag((size_t) m + 1), off((size_t) m + 1), cols((size_t) m), colmap((size_t) m);
 	static DevBuf<char> tmp;
 	for (int done = 0; done < n;) {
-		if (E.U.n == r_ub) {               /* the reference's test, literally (:88): A is the CURRENT matrix, U->n the total rank */
+		if (!E.want_L && E.U.n == r_ub) {  /* the reference's test, literally (:88): A is the CURRENT matrix, U->n the total rank */
 			LOG("\n[echelonize/GPLU] full rank reached\n");
 			break;
 		}
-		if (!early_abort_done && rows_since_last_pivot > 10 && rows_since_last_pivot > n / 100) {
+		if (!E.want_L && !early_abort_done && rows_since_last_pivot > 10 && rows_since_last_pivot > n / 100) {
 			LOG("\n[echelonize/GPLU] testing for early abort...\n");
 			if (test_completion_sparse(E, A, p, n))
 				break;
@@ -967,6 +979,7 @@ static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const s
 		DevBuf<int> d_rows;
 		d_rows.upload(p + done, (size_t) R, s);
 		E.solve_rows(A, d_rows.ptr, R, false);
+		const int batch_begin = done;
 		done += R;
 		DevBuf<i64> Sp;
 		DevBuf<int> Sj;
@@ -992,6 +1005,11 @@ static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const s
 		D.zero(s);
 		k_gplu_csr_to_dense<<<cdiv((size_t) R * 32, 256), 256, 0, s>>>(R, Sp.ptr, Sj.ptr, Sx.ptr, colmap.ptr, D.ptr, ld);
 		LAUNCHED(1);
+		DevBuf<i32> before;              /* L mode (lu.cu): the batch before it is echelonized */
+		if (E.want_L) {
+			before.alloc((size_t) R * ld);
+			CUDA_CHECK(cudaMemcpyAsync(before.ptr, D.ptr, (size_t) R * ld * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+		}
 		GpuTimer t;
 		t.start();
 		RrefResult res = dense_rref(D.ptr, R, C, ld, E.F);
@@ -1016,7 +1034,23 @@ static void finish_gplu(Engine &E, const DevCsr &A, const int *p, int n, const s
 		DevBuf<int> Rj;
 		DevBuf<i32> Rx;
 		i64 rnz = 0;
-		dense_rows_to_csr(Dr.ptr, ld, res.rank, C, d_pcol.ptr, d_own.ptr, cols.ptr, Rp, Rj, Rx, rnz);
+		if (E.want_L) {
+			/* rows of U in elimination order (row t = a row of the batch reduced by the rows before it): batch = Cm * Dr,
+			 * Cm = Pi^t Lc Uc, rows = Uc * Dr; L is read out of the final U (compute_L) */
+			const int ldc = std::max((res.rank + 3) & ~3, 4);
+			DevBuf<i32> Cm((size_t) R * ldc), Dlu((size_t) res.rank * ld);
+			dense_gather_columns(before.ptr, ld, R, d_pcol.ptr, res.rank, Cm.ptr, ldc);
+			std::vector<int> lu_row;
+			dense_lu_fullcol(Cm.ptr, R, res.rank, ldc, E.F, lu_row);
+			dense_lu_rows(Cm.ptr, ldc, res.rank, lu_row, Dr.ptr, ld, C, Dlu.ptr, ld, E.F);
+			dense_rows_to_csr(Dlu.ptr, ld, res.rank, C, d_pcol.ptr, nullptr, cols.ptr, Rp, Rj, Rx, rnz);
+			for (int local : lu_row) {
+				const int row = p[batch_begin + local];
+				E.p_struct.push_back(p_in ? p_in[row] : row);
+			}
+		} else {
+			dense_rows_to_csr(Dr.ptr, ld, res.rank, C, d_pcol.ptr, d_own.ptr, cols.ptr, Rp, Rj, Rx, rnz);
+		}
 		append_device_rows(E, Rp, Rj, Rx, res.rank, rnz);
 		rows_since_last_pivot = 0;
 		early_abort_done = false;
@@ -1048,7 +1082,10 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	for (DenseBlock &blk : E.blocks) {
 		Piece pc;
 		pc.rows = blk.rr;
-		dense_rows_to_csr(blk.D.ptr, blk.ld, blk.rr, E.Sm0, blk.d_pivcol.ptr, blk.d_own.ptr, E.d_q0.ptr, pc.p, pc.j, pc.x, pc.nnz);
+		if (blk.Dlu.ptr)       /* L mode: unit upper triangular rows, only the row's own pivot is implied */
+			dense_rows_to_csr(blk.Dlu.ptr, blk.ld, blk.rr, E.Sm0, blk.d_pivcol.ptr, nullptr, E.d_q0.ptr, pc.p, pc.j, pc.x, pc.nnz);
+		else
+			dense_rows_to_csr(blk.D.ptr, blk.ld, blk.rr, E.Sm0, blk.d_pivcol.ptr, blk.d_own.ptr, E.d_q0.ptr, pc.p, pc.j, pc.x, pc.nnz);
 		total += pc.nnz;
 		pieces.push_back(std::move(pc));
 	}
@@ -1057,6 +1094,16 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	struct spasm_csr *U = spasm_csr_alloc(std::max(rank, n_rows_alloc), E.m, std::max<i64>(total, 1), E.prime, true);
 	int *qinv = (int *) spasm_malloc((i64) std::max(E.m, 1) * sizeof(int));
 	E.Uqinv.download(qinv, (size_t) E.m, s);
+	int *Lp = NULL;                   /* L mode: fact->p, row of the input behind every row of U */
+	if (E.want_L) {
+		if ((int) (E.p_struct.size() + E.p_dense.size()) != rank || (int) E.p_struct.size() != E.U.n)
+			errx(1, "[spasm-b200] internal: %zu + %zu rows of origin for %d + %d pivots", E.p_struct.size(), E.p_dense.size(), E.U.n, E.dense_rank);
+		Lp = (int *) spasm_malloc((i64) std::max(rank, 1) * sizeof(int));
+		for (int t = 0; t < E.U.n; t++)
+			Lp[t] = E.p_struct[t];
+		for (int t = 0; t < E.dense_rank; t++)
+			Lp[E.U.n + t] = E.p_dense[t];
+	}
 	if (E.lazy_rows > 0) {
 		/* The first lazy_rows rows of U are in column order (lazy schedule, extract_structural).  Put them in
 		 * (level, column) order like the eager path does: the levels came out of the first solve pass; if no solve
@@ -1097,6 +1144,8 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 			memcpy(U->j + at, hj.data() + hp[r], (size_t) len * sizeof(int));
 			memcpy(U->x + at, hx.data() + hp[r], (size_t) len * sizeof(i32));
 			qinv[hj[hp[r]]] = t;              /* the pivot is the first entry of the row */
+			if (Lp)
+				Lp[t] = E.p_struct[r];
 			at += len;
 		}
 		U->p[E.U.n] = at;
@@ -1135,7 +1184,7 @@ static struct spasm_lu *assemble(Engine &E, int n_rows_alloc)
 	fact->L = NULL;
 	fact->U = U;
 	fact->qinv = qinv;
-	fact->p = NULL;
+	fact->p = Lp;
 	fact->Ltmp = NULL;
 	lap("trim");
 	return fact;
@@ -1156,7 +1205,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 	if (opts->complete)
 		opts->L = 1;
 	if (opts->L)
-		errx(1, "[spasm-b200] opts->L / opts->complete (PLUQ with L) is not part of the B200 echelonization path (DESIGN.md, out of scope)");
+		opts->enable_tall_and_skinny = 0;       /* echelonize.c:489-490 ("for now") */
 	if (opts->dense_block_size <= 0)
 		errx(1, "[spasm-b200] dense_block_size must be positive");
 
@@ -1171,6 +1220,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 		}
 	};
 	E.init(m, dA0.prime);
+	E.want_L = opts->L != 0;
 	lap("init");
 	DevCsr dS;                       /* current Schur complement once a round has run */
 	const DevCsr *cur = &dA0;
@@ -1208,7 +1258,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 		spec.discard(E);                 /* sparse after all: the finisher's batch is not needed */
 		LOG("Schur complement is %d x %d, estimated density : %.2f\n", n - npiv, m - E.U.n, density);
 		DevCsr S;
-		schur_sparse(E, *cur, p.data() + npiv, n - npiv, S);
+		schur_sparse(E, *cur, p.data() + npiv, n - npiv, S, nullptr);
 		lap("schur_sparse");
 		std::vector<int> p_out((size_t) (n - npiv));
 		for (int k = 0; k < n - npiv; k++) {
@@ -1242,7 +1292,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			finish_lowrank(E, *cur, p.data() + npiv, n - npiv, opts, &spec);
 		} else if (opts->enable_dense && density > opts->sparsity_threshold) {
 			st.pub.finish = 2;
-			finish_dense(E, *cur, p.data() + npiv, n - npiv, opts, &spec);
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, opts, &spec, p_in.empty() ? NULL : p_in.data());
 		} else if (opts->enable_GPLU) {
 			/* The reference finishes row by row (echelonize_GPLU, echelonize.c:54-187): leftmost pivot of each
 			 * reduced row.  That rule selects the column rank profile of the Schur complement, which is what
@@ -1252,7 +1302,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			st.pub.finish = 3;
 			static const bool gplu_dense = getenv("SPASM_B200_GPLU_DENSE") != NULL;
 			if (!gplu_dense && comm_world() == 1) {
-				finish_gplu(E, *cur, p.data() + npiv, n - npiv, opts);
+				finish_gplu(E, *cur, p.data() + npiv, n - npiv, opts, p_in.empty() ? NULL : p_in.data());
 				lap("finish");
 				return;
 			}
@@ -1273,7 +1323,7 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 			}
 			struct echelonize_opts o2 = *opts;
 			o2.enable_tall_and_skinny = 0;
-			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2, &spec);
+			finish_dense(E, *cur, p.data() + npiv, n - npiv, &o2, &spec, p_in.empty() ? NULL : p_in.data());
 		} else {
 			LOG("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
 		}
@@ -1330,6 +1380,8 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 		fprintf(stderr, "[trace] upload + echelonize_core %8.3f ms\n", 1e3 * (spasm_wtime() - start));
 	}
 	struct spasm_lu *fact = assemble(E, 0);
+	if (opts->L)
+		compute_L(fact, dA0, opts->complete != 0);
 	stats().pub.ms_device_echelonize = timer.stop_ms();
 	stats().pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
 	LOG("[echelonize] Done in %.3fs. Rank %d, %" PRId64 " nz in basis\n", spasm_wtime() - start, fact->U->n, spasm_nnz(fact->U));

@@ -1,4 +1,5 @@
 #include "engine.cuh"
+#include "lu.cuh"
 #include "stats.cuh"
 
 namespace sb {
@@ -22,6 +23,9 @@ void Engine::init(int m_, i64 prime_)
 	blocks.clear();
 	dense_rank = 0;
 	Sm0 = 0;
+	want_L = false;
+	p_struct.clear();
+	p_dense.clear();
 }
 
 void Engine::rebuild_schedule()
@@ -129,7 +133,7 @@ void Engine::gather_q0(i32 *S, int ldS)
 	panel_gather_dense(panel, d_q0.ptr, Sm0, S, ldS);
 }
 
-int Engine::absorb_block(i32 *B, int rows, int ldB)
+int Engine::absorb_block(i32 *B, int rows, int ldB, bool with_lu)
 {
 	if (rows <= 0 || Sm0 <= 0)
 		return 0;
@@ -182,7 +186,13 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 		dense_gather_columns(B, ldB, rows, d_cols.ptr, remaining, Bc.ptr, lds);
 		src = Bc.ptr;
 	}
-	RrefResult res = dense_rref(const_cast<i32 *>(src), rows, compact ? remaining : Sm0, lds, F);
+	const int width = compact ? remaining : Sm0;
+	DevBuf<i32> before;               /* L mode: the block as it is before the echelonization (lu.cu: B = C * R) */
+	if (with_lu) {
+		before.alloc((size_t) rows * lds);
+		CUDA_CHECK(cudaMemcpyAsync(before.ptr, src, (size_t) rows * lds * sizeof(i32), cudaMemcpyDeviceToDevice, s));
+	}
+	RrefResult res = dense_rref(const_cast<i32 *>(src), rows, width, lds, F);
 	if (res.rank > 0) {
 		DenseBlock blk;
 		blk.rr = res.rank;
@@ -208,6 +218,17 @@ int Engine::absorb_block(i32 *B, int rows, int ldB)
 		if (blk.rr >= 64 && umma_gemm_available(F)) {
 			blk.Dpack.alloc(umma_packed_bytes(Sm0, blk.rr, umma_limbs(F)));
 			umma_pack(blk.D.ptr, blk.ld, Sm0, blk.rr, false, blk.Dpack.ptr, F);
+		}
+		if (with_lu) {
+			/* C = (block before)[:, pivot columns];  C = Pi^t Lc Uc;  rows for U = Uc * D */
+			DevBuf<int> d_pc;
+			d_pc.upload(res.pivcol.data(), res.pivcol.size(), s);
+			const int ldc = std::max((blk.rr + 3) & ~3, 4);
+			DevBuf<i32> C((size_t) rows * ldc);
+			dense_gather_columns(before.ptr, lds, rows, d_pc.ptr, blk.rr, C.ptr, ldc);
+			dense_lu_fullcol(C.ptr, rows, blk.rr, ldc, F, blk.lu_row);
+			blk.Dlu.alloc((size_t) blk.rr * blk.ld);
+			dense_lu_rows(C.ptr, ldc, blk.rr, blk.lu_row, blk.D.ptr, blk.ld, Sm0, blk.Dlu.ptr, blk.ld, F);
 		}
 		sync();
 		dense_rank += blk.rr;

@@ -22,6 +22,10 @@ struct DenseBlock {
 	DevBuf<int> d_pivcol;
 	DevBuf<unsigned char> d_own;     /* flag per q0 column: pivot of this block */
 	DevBuf<int8_t> Dpack;            /* D split into int8 limb planes, tile-packed for the tensor cores (umma_gemm.cu); may be empty */
+	/* L mode only (lu.cu): the rows that go to U, unit upper triangular on the pivot columns (Uc * D), and the row of the
+	 * block each one was obtained from */
+	DevBuf<i32> Dlu;
+	std::vector<int> lu_row;
 };
 
 struct Engine {
@@ -34,6 +38,10 @@ struct Engine {
 	DepGraph G;                      /* forward dependency graph of U, scheduled */
 	bool G_ready = false;
 	int lazy_rows = 0;               /* the first lazy_rows rows of U are in column order: assemble() puts them in level order */
+	/* L mode (opts->L): row of the input matrix each row of the echelon form was obtained from (fact->p) */
+	bool want_L = false;
+	std::vector<int> p_struct;       /* per row of U */
+	std::vector<int> p_dense;        /* per dense row, block after block */
 	/* dense part, over the columns that are non-pivotal after the structural rounds */
 	bool dense_ready = false;
 	int Sm0 = 0;
@@ -58,8 +66,9 @@ struct Engine {
 	void account_bytes(int R);
 	/* gather the q0 columns of the panel into a dense row-major block (R x Sm0, ld = ldS) */
 	void gather_q0(i32 *S, int ldS);
-	/* reduce a dense block by the dense rows found so far, echelonize it, keep its pivot rows. Returns rr. */
-	int absorb_block(i32 *B, int rows, int ldB);
+	/* reduce a dense block by the dense rows found so far, echelonize it, keep its pivot rows. Returns rr.
+	 * with_lu (L mode): the block also keeps its pivot rows in unit-upper-triangular form and their rows of origin. */
+	int absorb_block(i32 *B, int rows, int ldB, bool with_lu = false);
 };
 
 int comm_world();

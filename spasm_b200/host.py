@@ -62,6 +62,19 @@ class LuHandle:
         m = self.ptr.contents.U.contents.m
         return np.ctypeslib.as_array(self.ptr.contents.qinv, shape=(m,)).copy() if m else np.zeros(0, np.int32)
 
+    @property
+    def L(self) -> dict | None:
+        """n x rank factor of the L mode (opts.L / opts.complete), None otherwise"""
+        return abi.csr_to_numpy(self.ptr.contents.L) if self.ptr.contents.L else None
+
+    @property
+    def p(self) -> np.ndarray | None:
+        """p[k] = row of the input behind row k of U (L mode)"""
+        r = self.rank
+        if not self.ptr.contents.p:
+            return None
+        return np.ctypeslib.as_array(self.ptr.contents.p, shape=(r,)).copy() if r else np.zeros(0, np.int32)
+
 
 def compress(lib, trip) -> CsrHandle:
     """spasm_triplet_alloc + spasm_add_entry (bulk) + spasm_compress  (reference: tools/rank.c:83-90).
@@ -117,6 +130,20 @@ def echelonize(lib, A: CsrHandle, opts: abi.EchelonizeOpts | None = None) -> LuH
     if opts is None:
         opts = default_opts(lib)
     return LuHandle(lib, lib.spasm_echelonize(A.ptr, C.byref(opts)))
+
+
+def factorization_verify(lib, A: CsrHandle, fact: LuHandle, seed: int) -> bool:
+    """spasm_factorization_verify (reference: src/spasm_certificate.c:164): x*A == (x*L)*U for a random x on the pivotal rows"""
+    return bool(lib.spasm_factorization_verify(A.ptr, fact.ptr, seed))
+
+
+def solve(lib, fact: LuHandle, b: np.ndarray):
+    """spasm_solve (reference: src/spasm_solve.c:13): x with x*A == b, and whether it exists"""
+    n = fact.ptr.contents.L.contents.n
+    b = np.ascontiguousarray(b, np.int32)
+    x = np.zeros(max(n, 1), np.int32)
+    ok = lib.spasm_solve(fact.ptr, b.ctypes.data_as(abi.i32_p), x.ctypes.data_as(abi.i32_p))
+    return x[:n], bool(ok)
 
 
 def rank(lib, A: CsrHandle, opts=None) -> int:

@@ -5,8 +5,10 @@ the GPU box inside oracle/_ref/).  They are run the way tests/CMakeLists.txt:20-
 
 CPU tier: the programs that only exercise host code of the boundary (field, PRNG, SHA-256, permutations, transpose,
 spmv, sub-matrix, the one-row triangular solves).  GPU tier: echelonize, kernel, schur, schur_dense,
-dense_rref_ffpack, sparse_utsolve -- they call spasm_echelonize & co. (CUDA) and CHECK the result with the host
-verifiers of csrc/host/verify.c, i.e. with the reference's own row-by-row arithmetic.
+dense_rref_ffpack, sparse_utsolve, sparse_lu_usolve and the L path (lu, solve, gesv, rank_cert, dense_lu_ffpack:
+spasm_echelonize with opts->L / opts->complete, spasm_ffpack_LU) -- they call spasm_echelonize & co. (CUDA) and CHECK
+the result with the host verifiers of csrc/host/verify.c and solve.c, i.e. with the reference's own row-by-row
+arithmetic.
 
 The known answers in tests/golden/expected/ are the reference's tests/Expected/{prng,hash,gaxpy.1,submatrix.1}."""
 import os
@@ -98,14 +100,19 @@ def test_upper_triangular_solves(prog):
             check(run(prog, "--modulus", str(p), stdin=sms_of(name)), f"{prog} {name} mod {p}")
 
 
+@pytest.mark.parametrize("prog", ["dense_lsolve", "sparse_lsolve"])
+def test_lower_triangular_solves(prog):
+    """tests/CMakeLists.txt:188-189 (spasm_dense_back_solve, the solve behind spasm_solve's L step)"""
+    for name in ("l1", "lower_trapeze"):
+        for p in MODULI:
+            check(run(prog, "--modulus", str(p), stdin=sms_of(name)), f"{prog} {name} mod {p}")
+
+
 # ---------------------------------------------------------------- programs that run the CUDA path
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("prog", ["echelonize", "kernel", "schur", "schur_dense", "dense_rref_ffpack", "sparse_utsolve"])
-def test_reference_program_on_every_fixture_and_modulus(prog):
-    """tests/CMakeLists.txt spasm_run_tests_mod: 32 fixtures x 6 moduli"""
+def _sweep(prog, moduli):
     import concurrent.futures
-    jobs = [(name, p) for name in fixture_names() for p in MODULI]
+    jobs = [(name, p) for name in fixture_names() for p in moduli]
     inputs = {name: sms_of(name) for name in fixture_names()}
 
     def one(job):
@@ -118,7 +125,28 @@ def test_reference_program_on_every_fixture_and_modulus(prog):
                 break                       # a real failure; a start-up refusal (many contexts created at once) is retried once
         return (name, p, r.returncode, r.stdout[-200:], r.stderr[-300:])
 
-    # every run is its own process with its own CUDA context (~1 s of start-up each): eight at a time share the GPU
+    # every run is its own process with its own CUDA context (~1 s of start-up each): six at a time share the GPU
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         failures = [f for f in ex.map(one, jobs) if f is not None]
     assert not failures, f"{len(failures)} failing runs, first: {failures[:3]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", ["echelonize", "kernel", "schur", "schur_dense", "dense_rref_ffpack", "sparse_utsolve"])
+def test_reference_program_on_every_fixture_and_modulus(prog):
+    """tests/CMakeLists.txt spasm_run_tests_mod: 32 fixtures x 6 moduli"""
+    _sweep(prog, MODULI)
+
+
+# The programs of the L path (tests/CMakeLists.txt:192,218-225).  A sweep of 32 fixtures x 6 moduli is 192 processes,
+# about two minutes of GPU-box time per program (CUDA start-up of each process); by default every program runs all the
+# fixtures on two of the six moduli, rotated so that the six are covered, and `lu` (the complete factorization) on
+# three.  SPASM_B200_FULL_SWEEP=1 runs the full products (done once per round: tools/r2_job12.sh, all green).
+L_PATH = {"lu": (3, 65537, 4294967291), "solve": (257, 67108859), "gesv": (65537, 189812507), "rank_cert": (3, 4294967291),
+          "dense_lu_ffpack": (257, 189812507), "sparse_lu_usolve": (65537, 67108859)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", sorted(L_PATH))
+def test_reference_program_of_the_L_path(prog):
+    _sweep(prog, MODULI if os.environ.get("SPASM_B200_FULL_SWEEP") else L_PATH[prog])
