@@ -7,27 +7,26 @@
  * against this file and link against libspasm_b200.so unchanged: its
  * tools/rank.c, tools/echelonize.c, tools/kernel.c, and its test programs
  * echelonize, kernel, schur, schur_dense, dense_rref_ffpack, sparse_utsolve,
- * sparse_usolve, dense_usolve, GFp, prng, sha, spmv, submatrix, transpose,
- * mat_perm, vec_perm (oracle/Makefile: b200_tools, b200_tests).
+ * sparse_usolve, dense_usolve, sparse_lsolve, dense_lsolve, sparse_lu_usolve,
+ * lu, solve, gesv, rank_cert, dense_lu_ffpack, GFp, prng, sha, spmv,
+ * submatrix, transpose, mat_perm, vec_perm (oracle/Makefile: b200_tools,
+ * b200_tests; run by tests/test_reference_tests.py).
  *
- * NOT provided (22 symbols of the reference's header are reduced to 8):
- *   - declared here, exported, but aborting with errx(1, ...): spasm_solve,
- *     spasm_gesv, the rank-certificate functions, spasm_factorization_verify,
- *     spasm_ffpack_LU, and opts->L / opts->complete in spasm_echelonize (the
- *     PLUQ path) -- tools/solve, rank --certificate, the
- *     reference tests lu / solve / gesv / rank_cert / dense_lu_ffpack link but
- *     do not run;
- *   - neither declared nor exported: spasm_dulmage_mendelsohn,
- *     spasm_maximum_matching, spasm_strongly_connected_components,
- *     spasm_structural_rank, spasm_submatching, spasm_permute_row_matching,
- *     spasm_permute_column_matching, spasm_save_pnm (independent graph library
- *     and bitmap output, never called by the echelonization) -- tools/dm,
- *     tools/bitmap and the tests dm / matching / scc do not link.
+ * The L side (opts->L / opts->complete, spasm_ffpack_LU, spasm_solve,
+ * spasm_gesv, rank certificates, spasm_factorization_verify) is provided
+ * since round 2 (csrc/gpu/lu.cu, csrc/host/solve.c).
+ *
+ * NOT provided -- neither declared nor exported: spasm_dulmage_mendelsohn,
+ * spasm_maximum_matching, spasm_strongly_connected_components,
+ * spasm_structural_rank, spasm_submatching, spasm_permute_row_matching,
+ * spasm_permute_column_matching, spasm_save_pnm (independent graph library
+ * and bitmap output, never called by the echelonization) -- tools/dm,
+ * tools/bitmap and the tests dm / matching / scc do not link.
  *
  * What differs is behind the boundary: spasm_echelonize(), spasm_rref(),
- * spasm_kernel(), the spasm_schur*() family, spasm_pivots_extract_structural()
- * and spasm_ffpack_rref() run as CUDA kernels for sm_100a.  There is no CPU
- * implementation of these entry points in the library: without a usable
+ * spasm_kernel(), the spasm_schur*() family, spasm_pivots_extract_structural(),
+ * spasm_ffpack_rref() and spasm_ffpack_LU() run as CUDA kernels for sm_100a.
+ * There is no CPU implementation of these entry points in the library: without a usable
  * CUDA device they abort with errx(1, ...), the reference's error convention
  * (reference: src/spasm_util.c:65-87).
  *

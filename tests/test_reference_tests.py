@@ -110,9 +110,11 @@ def test_lower_triangular_solves(prog):
 
 # ---------------------------------------------------------------- programs that run the CUDA path
 
-def _sweep(prog, moduli):
+FULL_SWEEP = bool(os.environ.get("SPASM_B200_FULL_SWEEP"))
+
+
+def _sweep(prog, jobs):
     import concurrent.futures
-    jobs = [(name, p) for name in fixture_names() for p in moduli]
     inputs = {name: sms_of(name) for name in fixture_names()}
 
     def one(job):
@@ -131,22 +133,24 @@ def _sweep(prog, moduli):
     assert not failures, f"{len(failures)} failing runs, first: {failures[:3]}"
 
 
+def _jobs(prog_index: int, per_fixture: int):
+    """32 fixtures x 6 moduli (tests/CMakeLists.txt spasm_run_tests_mod) is 192 processes, two minutes of GPU-box time per
+    program, all of it CUDA start-up.  By default only `echelonize` runs the full product; the other programs run every
+    fixture on `per_fixture` of the six moduli, rotated with the fixture and the program so that each program meets all
+    six moduli and each fixture meets all six across the programs.  SPASM_B200_FULL_SWEEP=1 runs the full product for
+    every program (tools/r2_job12.sh; green for all twelve programs in round 2)."""
+    names = fixture_names()
+    if FULL_SWEEP or per_fixture >= len(MODULI):
+        return [(name, p) for name in names for p in MODULI]
+    return [(name, MODULI[(k + prog_index + t * 3) % len(MODULI)]) for k, name in enumerate(names) for t in range(per_fixture)]
+
+
+# program -> moduli per fixture in the default run.  L path: tests/CMakeLists.txt:192,218-225.
+GPU_PROGRAMS = {"echelonize": 6, "kernel": 2, "lu": 2, "schur": 1, "schur_dense": 1, "dense_rref_ffpack": 1, "sparse_utsolve": 1,
+                "sparse_lu_usolve": 1, "solve": 1, "gesv": 1, "rank_cert": 1, "dense_lu_ffpack": 1}
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("prog", ["echelonize", "kernel", "schur", "schur_dense", "dense_rref_ffpack", "sparse_utsolve"])
-def test_reference_program_on_every_fixture_and_modulus(prog):
-    """tests/CMakeLists.txt spasm_run_tests_mod: 32 fixtures x 6 moduli"""
-    _sweep(prog, MODULI)
-
-
-# The programs of the L path (tests/CMakeLists.txt:192,218-225).  A sweep of 32 fixtures x 6 moduli is 192 processes,
-# about two minutes of GPU-box time per program (CUDA start-up of each process); by default every program runs all the
-# fixtures on two of the six moduli, rotated so that the six are covered, and `lu` (the complete factorization) on
-# three.  SPASM_B200_FULL_SWEEP=1 runs the full products (done once per round: tools/r2_job12.sh, all green).
-L_PATH = {"lu": (3, 65537, 4294967291), "solve": (257, 67108859), "gesv": (65537, 189812507), "rank_cert": (3, 4294967291),
-          "dense_lu_ffpack": (257, 189812507), "sparse_lu_usolve": (65537, 67108859)}
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("prog", sorted(L_PATH))
-def test_reference_program_of_the_L_path(prog):
-    _sweep(prog, MODULI if os.environ.get("SPASM_B200_FULL_SWEEP") else L_PATH[prog])
+@pytest.mark.parametrize("prog", list(GPU_PROGRAMS))
+def test_reference_program_on_the_fixtures(prog):
+    _sweep(prog, _jobs(list(GPU_PROGRAMS).index(prog), GPU_PROGRAMS[prog]))
