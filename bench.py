@@ -488,7 +488,15 @@ def main() -> None:
             v = torch.tensor([res[k] for k in keys], dtype=torch.float64, device="cuda")
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
             return {k: float(x) for k, x in zip(keys, v)}
+        legAll = None
+        if world > 1:
+            # first with every rank receiving the full result (one group of ncclBroadcast), then gathered on rank 0 only
+            # (ncclSend / ncclRecv; the other ranks skip a download they do not use): the second is the leg's value
+            legAll = scale_leg(L, host, spasm_b200, barrier, args.scale_leg_steps, args.scale_leg_scale, reduce_max)
+            L.spasm_b200_comm_result_root(0)
         legN = scale_leg(L, host, spasm_b200, barrier, args.scale_leg_steps, args.scale_leg_scale, reduce_max)
+        if world > 1:
+            L.spasm_b200_comm_result_root(-1)
 
     if rank == 0:
         if legN is not None:
@@ -496,9 +504,14 @@ def main() -> None:
                    "echelonize_s": legN["ech"], "rref_s": legN["rref"], "kernel_s": legN["kernel"], "steps": legN["steps"],
                    "rank": legN["rank"], "rref_nnz": legN["rref_nnz"], "kernel_dim": legN["kernel_dim"],
                    "nccl_bytes_per_step": legN["nccl_bytes_per_step"],
-                   "collective": "ncclAllGather (piece sizes) + one group of ncclBroadcast, one per result piece (variable length, from its owner)",
+                   "collective": ("ncclAllGather (piece sizes) + one group of ncclSend / ncclRecv, one per result piece (variable length), to rank 0: "
+                                  "the result (a host matrix) is materialised on rank 0" if world > 1 else "none (one rank)"),
                    "sharding": "rows of U (rref) and non-pivotal columns (kernel) in contiguous slices, U replicated; echelonize: rows of the solve batches",
                    "timing": "host wall clock around the three C-ABI calls (they return host matrices), barrier on both sides, max over ranks"}
+            if legAll is not None:
+                leg["every_rank_gets_the_result"] = {"value": legAll["total"], "rref_s": legAll["rref"], "kernel_s": legAll["kernel"],
+                                                     "nccl_bytes_per_step": legAll["nccl_bytes_per_step"],
+                                                     "collective": "one group of ncclBroadcast, one per result piece, from its owner; every rank downloads the full host matrix"}
             single = leg1 if leg1 is not None else (legN if world == 1 else None)
             if single is not None:
                 leg["single_gpu_value"] = single["total"]

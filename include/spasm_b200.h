@@ -87,6 +87,10 @@ void spasm_b200_comm_unique_id(void *out128);
 void spasm_b200_comm_init(int rank, int world, const void *unique_id128);
 void spasm_b200_comm_destroy(void);
 int  spasm_b200_comm_world(void);
+/* root >= 0: spasm_rref and spasm_kernel GATHER their sharded result on that rank (ncclSend / ncclRecv); the other ranks
+ * return a matrix of the right shape with no entries and skip the download of a result they do not use.  root < 0
+ * (default): every rank returns the full result (one group of ncclBroadcast). */
+void spasm_b200_comm_result_root(int root);
 
 /* structural pivot pairs (row of the ORIGINAL matrix, column) of the last spasm_echelonize call,
  * round after round; returns their number.  Pass NULL to query the count. */

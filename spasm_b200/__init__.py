@@ -36,6 +36,7 @@ EXTRA_PROTOTYPES = {
     "spasm_b200_comm_init": (None, [C.c_int, C.c_int, C.c_void_p]),
     "spasm_b200_comm_destroy": (None, []),
     "spasm_b200_comm_world": (C.c_int, []),
+    "spasm_b200_comm_result_root": (None, [C.c_int]),
     "spasm_b200_gemm_sub": (None, [C.c_int64, C.c_int, C.c_int, C.c_int, abi.i32_p, abi.i32_p, abi.i32_p, C.c_int]),
     "spasm_b200_gemm_time": (C.c_double, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spasm_b200_prng_stream": (None, [C.c_int64, C.c_uint64, C.c_uint32, C.c_int, abi.i32_p]),

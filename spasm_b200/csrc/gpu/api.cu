@@ -121,6 +121,20 @@ static void exchange_pieces(std::vector<HostPiece> &pieces)
 	comm_allgather_bytes(d_meta.ptr, per * sizeof(i64));
 	d_meta.download(meta.data(), meta.size(), s);
 	sync();
+	const int root = comm_result_root();
+	if (root >= 0 && me != root) {
+		/* gather to one rank (spasm_b200_comm_result_root): this rank only ships its pieces and returns an empty result */
+		comm_group_begin();
+		for (HostPiece &pc : pieces) {
+			comm_send_bytes(pc.p.ptr, ((size_t) pc.rows + 1) * sizeof(i64), root);
+			comm_send_bytes(pc.j.ptr, (size_t) pc.nnz * sizeof(int), root);
+			comm_send_bytes(pc.x.ptr, (size_t) pc.nnz * sizeof(i32), root);
+		}
+		comm_group_end();
+		sync();
+		pieces.clear();
+		return;
+	}
 	std::vector<HostPiece> all;
 	for (int r = 0; r < world; r++) {
 		const i64 *mr = meta.data() + per * r;
@@ -144,6 +158,14 @@ static void exchange_pieces(std::vector<HostPiece> &pieces)
 		const i64 *mr = meta.data() + per * r;
 		for (i64 k = 0; k < mr[0]; k++, at++) {
 			HostPiece &pc = all[at];
+			if (root >= 0) {
+				if (r != me) {
+					comm_recv_bytes(pc.p.ptr, ((size_t) pc.rows + 1) * sizeof(i64), r);
+					comm_recv_bytes(pc.j.ptr, (size_t) pc.nnz * sizeof(int), r);
+					comm_recv_bytes(pc.x.ptr, (size_t) pc.nnz * sizeof(i32), r);
+				}
+				continue;
+			}
 			comm_bcast_bytes(pc.p.ptr, ((size_t) pc.rows + 1) * sizeof(i64), r);
 			comm_bcast_bytes(pc.j.ptr, (size_t) pc.nnz * sizeof(int), r);
 			comm_bcast_bytes(pc.x.ptr, (size_t) pc.nnz * sizeof(i32), r);

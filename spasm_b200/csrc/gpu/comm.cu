@@ -30,11 +30,14 @@ static struct {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 	ncclComm_t comm = nullptr;
 	int rank = 0, world = 1;
+	int result_root = -1;      /* >= 0: spasm_rref / spasm_kernel materialise their result on this rank only */
 } g_nccl;
 
 static void nccl_load()
@@ -52,6 +55,8 @@ static void nccl_load()
 	*(void **) &g_nccl.AllGather = dlsym(g_nccl.handle, "ncclAllGather");
 	*(void **) &g_nccl.GetErrorString = dlsym(g_nccl.handle, "ncclGetErrorString");
 	*(void **) &g_nccl.Broadcast = dlsym(g_nccl.handle, "ncclBroadcast");
+	*(void **) &g_nccl.Send = dlsym(g_nccl.handle, "ncclSend");
+	*(void **) &g_nccl.Recv = dlsym(g_nccl.handle, "ncclRecv");
 	*(void **) &g_nccl.GroupStart = dlsym(g_nccl.handle, "ncclGroupStart");
 	*(void **) &g_nccl.GroupEnd = dlsym(g_nccl.handle, "ncclGroupEnd");
 	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
@@ -109,6 +114,26 @@ void comm_bcast_bytes(void *buf, size_t bytes, int root)
 		stats().pub.nccl_bytes += (i64) bytes;
 }
 
+/* point-to-point halves of a gather to one rank (inside a group, like the broadcasts) */
+int comm_result_root() { return g_nccl.world > 1 ? g_nccl.result_root : -1; }
+void comm_send_bytes(const void *buf, size_t bytes, int peer)
+{
+	if (bytes == 0)
+		return;
+	if (!g_nccl.Send)
+		errx(1, "[spasm-b200] NCCL library lacks ncclSend");
+	NCCL_CHECK(g_nccl.Send(buf, bytes, 0 /* ncclInt8 */, peer, g_nccl.comm, ctx().stream));
+}
+void comm_recv_bytes(void *buf, size_t bytes, int peer)
+{
+	if (bytes == 0)
+		return;
+	if (!g_nccl.Recv)
+		errx(1, "[spasm-b200] NCCL library lacks ncclRecv");
+	NCCL_CHECK(g_nccl.Recv(buf, bytes, 0 /* ncclInt8 */, peer, g_nccl.comm, ctx().stream));
+	stats().pub.nccl_bytes += (i64) bytes;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -146,4 +171,6 @@ void spasm_b200_comm_destroy(void)
 }
 
 int spasm_b200_comm_world(void) { return g_nccl.world; }
+
+void spasm_b200_comm_result_root(int root) { g_nccl.result_root = root; }
 }

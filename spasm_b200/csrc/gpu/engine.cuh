@@ -79,5 +79,8 @@ void comm_allgather_bytes(void *buf, size_t bytes);
 void comm_group_begin();
 void comm_group_end();
 void comm_bcast_bytes(void *buf, size_t bytes, int root);
+int comm_result_root();
+void comm_send_bytes(const void *buf, size_t bytes, int peer);
+void comm_recv_bytes(void *buf, size_t bytes, int peer);
 
 }  // namespace sb

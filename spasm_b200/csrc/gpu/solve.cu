@@ -859,14 +859,30 @@ __device__ __forceinline__ void flow2_publish(const FlowPub &pb, const FlowMeta2
 	}
 }
 
+/* 1-D bulk copy (the TMA engine without a tensor map) of a column's blob of dependents' records into shared memory:
+ * one request of 832 bytes instead of 208 word loads by the prefetch warp, completion on an mbarrier */
+__device__ __forceinline__ uint32_t flow_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool flow_mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	             : "=r"(ok) : "r"(flow_smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+
 __global__ void __launch_bounds__(1024)
 k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, const i32 *__restrict__ val,
                     const i64 *__restrict__ rptr, const int *__restrict__ rdst,
                     int *pending, int *queue, int nscheduled, int *tail, int *ticket, int *done, int *error, int *doneflag,
-                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob, int nnodes)
+                    int4 *X, int ld4, int R4, Zp F, int *level_out, unsigned long long *hopstats, const FlowMeta2 *__restrict__ blob, int nnodes,
+                    int bulk_blob)
 {
 	__shared__ int s_node, s_next, s_capt;
-	__shared__ FlowMeta2 cur, dep[2][FLOW_MAXD];
+	__shared__ FlowMeta2 cur;
+	__shared__ __align__(16) FlowMeta2 dep[2][FLOW_MAXD];
+	__shared__ __align__(8) uint64_t dep_bar;
+	uint32_t dep_phase = 0;               /* prefetch warp: parity of the next completion of dep_bar */
 	unsigned n_certain = 0, n_released = 0, n_polled = 0;      /* how the CTA came by its columns (thread 0; development) */
 	__shared__ FlowPub pub;
 	const int tid = threadIdx.x, lane = tid & 31;
@@ -880,8 +896,11 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 #pragma unroll
 	for (int g = 0; g < FLOW2_G; g++)
 		fwd[g] = make_int4(0, 0, 0, 0);
-	if (tid == 0)
+	if (tid == 0) {
 		pub.valid = 0;
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flow_smem_u32(&dep_bar)), "r"(1));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	__syncthreads();
 	for (;;) {
 		/* ---- 1. the job */
@@ -1007,7 +1026,25 @@ k_panel_solve_flow2(const i64 *__restrict__ ptr, const int *__restrict__ src, co
 			/* ---- 2b. metadata of the dependents of c (one coalesced copy of the column's blob), and whether c is the
 			 * last dependency they wait for (the flags of their other dependencies) */
 			FlowMeta2 *dp = dep[buf];
-			{
+			if (bulk_blob) {
+				/* U's entries for the next hop, staged by the TMA engine: cp.async.bulk global -> shared, mbarrier expect_tx.
+				 * The buffer was last read (generic proxy) two hops ago, before several CTA barriers; the proxy fence orders
+				 * those reads before the asynchronous write. */
+				if (lane == 0) {
+					const uint32_t bytes = (uint32_t) (FLOW_MAXD * sizeof(FlowMeta2));
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(flow_smem_u32(&dep_bar)), "r"(bytes) : "memory");
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					             ::"r"(flow_smem_u32(dp)), "l"(blob + (size_t) c * FLOW_MAXD), "r"(bytes), "r"(flow_smem_u32(&dep_bar)) : "memory");
+				}
+				__syncwarp();
+				bool arrived = false;
+				for (int spin = 0; spin < (1 << 24) && !(arrived = flow_mbar_try_wait(&dep_bar, dep_phase)); spin++)
+					;
+				if (!arrived && lane == 0)
+					*error = 1;                   /* never seen; the host reports an internal error instead of hanging */
+				dep_phase ^= 1;
+			} else {
 				const int *gsrc = reinterpret_cast<const int *>(blob + (size_t) c * FLOW_MAXD);
 				int *gdst = reinterpret_cast<int *>(dp);
 #pragma unroll
@@ -1296,6 +1333,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			threads = R4 + 64 > 512 ? 1024 : R4 + 64 > 256 ? 512 : 256;
 			DevBuf<int> doneflag((size_t) n);
 			static const bool hoptrace = getenv("SPASM_B200_TRACE") != NULL;
+			static const bool no_bulk = getenv("SPASM_B200_FLOW2_NO_BULK") != NULL;      /* blob copied by the prefetch warp's own loads */
 			DevBuf<unsigned long long> hopstats(3);
 			hopstats.zero(s);
 			DevBuf<char> blob(((size_t) n * FLOW_MAXD + (size_t) n) * sizeof(FlowMeta2));
@@ -1309,7 +1347,7 @@ void panel_solve(const DepGraph &G, i32 *X, int ld, int R, const Zp &F)
 			k_panel_solve_flow2<<<blocks, threads, 0, s>>>(G.ptr.ptr, G.src.ptr, G.val.ptr, G.rptr.ptr, G.rdst.ptr, pending.ptr, queue.ptr,
 			                                          G.nscheduled, counters.ptr, counters.ptr + 1, counters.ptr + 2, counters.ptr + 3, doneflag.ptr,
 			                                          (int4 *) X, ld4, R4, F, G.levels_known ? nullptr : G.level.ptr, hoptrace ? hopstats.ptr : nullptr,
-			                                          (const FlowMeta2 *) blob.ptr, n);
+			                                          (const FlowMeta2 *) blob.ptr, n, no_bulk ? 0 : 1);
 			LAUNCHED(2);
 			KERNEL_CHECK();
 			stats().pub.ms_k_panel_solve += tk.stop_ms();      /* before doneflag goes out of scope: the stop synchronises */

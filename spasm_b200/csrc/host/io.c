@@ -15,29 +15,49 @@
 
 #define LINE_MAX_LEN 1024
 
+/* The stream is read to its end first (the reference reads to EOF too, warning about what follows the terminator):
+ * the SHA-256 is then one pass over the buffer and the entry lines can go to the GPU in one piece (csrc/gpu/ingest.cu). */
 struct reader {
-	FILE *f;
-	spasm_sha256_ctx sha;
-	bool hashing;
+	const char *text;
+	size_t bytes, pos;
 	i64 lineno;
 	char buf[LINE_MAX_LEN];
 };
 
-/* fetch the next line; returns false at end of file (reference: src/spasm_io.c:11-26) */
+static char *slurp(FILE *f, size_t *bytes)
+{
+	size_t cap = (size_t) 1 << 20, len = 0;
+	char *text = spasm_malloc(cap);
+	for (;;) {
+		size_t got = fread(text + len, 1, cap - len, f);
+		len += got;
+		if (got == 0) {
+			if (ferror(f))
+				err(1, "[spasm_triplet_load] impossible to read the input");
+			break;
+		}
+		if (len == cap) {
+			cap *= 2;
+			text = spasm_realloc(text, cap);
+		}
+	}
+	*bytes = len;
+	return text;
+}
+
+/* fetch the next line into r->buf; returns false at end of input (reference: src/spasm_io.c:11-26) */
 static bool next_line(struct reader *r)
 {
-	if (fgets(r->buf, LINE_MAX_LEN, r->f) == NULL) {
-		if (feof(r->f))
-			return false;
-		err(1, "[spasm_triplet_load] impossible to read line %" PRId64, r->lineno);
-	}
-	size_t len = strlen(r->buf);
-	if (len == 0)
-		errx(1, "[spasm_triplet_load] empty line %" PRId64, r->lineno);
-	if (r->buf[len - 1] != '\n' && !feof(r->f))
+	if (r->pos >= r->bytes)
+		return false;
+	const char *line = r->text + r->pos;
+	const char *nl = memchr(line, '\n', r->bytes - r->pos);
+	size_t len = nl ? (size_t) (nl - line) + 1 : r->bytes - r->pos;
+	if (len > LINE_MAX_LEN - 1)       /* what fgets(buf, LINE_MAX_LEN) cannot hold in one piece */
 		errx(1, "[spasm_triplet_load] line %" PRId64 " too long (> %d)", r->lineno, LINE_MAX_LEN);
-	if (r->hashing)
-		spasm_SHA256_update(&r->sha, r->buf, len);
+	memcpy(r->buf, line, len);
+	r->buf[len] = 0;
+	r->pos += len;
 	return true;
 }
 
@@ -93,6 +113,25 @@ static bool parse_entry(const char *s, int *i, int *j, i64 *x)
  */
 /* csrc/gpu/device.cu: starts the creation of the CUDA context on a helper thread (once; no effect without a GPU) */
 void spasm_b200_warmup_async(void);
+int spasm_b200_device_count(void);
+/* csrc/gpu/ingest.cu: the entry lines parsed on the GPU */
+i64 spasm_b200_ingest_entries(const char *text, size_t bytes, struct spasm_triplet *T, bool matrixmarket, i64 declared, i64 first_lineno);
+
+/* Entry lines go to the GPU when there is at least this much text (SPASM_B200_INGEST_MIN_BYTES, default 1 MB: below
+ * that the host loop is faster than the round trip) and a CUDA device is present; SPASM_B200_INGEST=host / gpu forces
+ * one side.  I/O is not part of the echelonization path: programs that only read, transpose or print matrices keep
+ * working without a GPU. */
+static bool ingest_on_gpu(size_t bytes)
+{
+	const char *mode = getenv("SPASM_B200_INGEST");
+	if (mode != NULL && strcmp(mode, "host") == 0)
+		return false;
+	if (mode != NULL && strcmp(mode, "gpu") == 0)
+		return true;
+	const char *min = getenv("SPASM_B200_INGEST_MIN_BYTES");
+	size_t threshold = min ? (size_t) atoll(min) : ((size_t) 1 << 20);
+	return bytes >= threshold && spasm_b200_device_count() > 0;
+}
 
 struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash)
 {
@@ -102,10 +141,12 @@ struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash)
 	spasm_b200_warmup_async();
 	double start = spasm_wtime();
 	struct reader r;
-	r.f = f;
-	r.hashing = (hash != NULL);
+	size_t bytes = 0;
+	char *text = slurp(f, &bytes);
+	r.text = text;
+	r.bytes = bytes;
+	r.pos = 0;
 	r.lineno = 0;
-	spasm_SHA256_init(&r.sha);
 
 	if (!next_line(&r))
 		errx(1, "[spasm_triplet_load] empty file\n");
@@ -138,6 +179,13 @@ struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash)
 	struct spasm_triplet *T = spasm_triplet_alloc(n, m, declared_nnz, prime, prime != -1);
 	bool finished = false;
 	i64 entries = 0;
+	if (ingest_on_gpu(r.bytes - r.pos)) {
+		i64 garbage = spasm_b200_ingest_entries(r.text + r.pos, r.bytes - r.pos, T, mm, declared_nnz, r.lineno + 1);
+		if (garbage > 0)
+			warnx("[spasm_load] garbage detected near end of file");
+		r.pos = r.bytes;
+		finished = true;
+	}
 	for (;;) {
 		r.lineno += 1;
 		bool got = next_line(&r);
@@ -175,13 +223,18 @@ struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash)
 	}
 
 	if (hash != NULL) {
-		i64 size = (((i64) r.sha.Nh) << 29) + r.sha.Nl / 8;
-		spasm_SHA256_final(hash, &r.sha);
+		/* the digest covers every byte read, like the reference's line-by-line updates (io.c:23-24) */
+		spasm_sha256_ctx sha;
+		spasm_SHA256_init(&sha);
+		spasm_SHA256_update(&sha, text, bytes);
+		i64 size = (i64) bytes;
+		spasm_SHA256_final(hash, &sha);
 		fprintf(stderr, "[spasm_triplet_load] sha256(matrix) = ");
 		for (int k = 0; k < 32; k++)
 			fprintf(stderr, "%02x", hash[k]);
 		fprintf(stderr, " / size = %" PRId64 " bytes\n", size);
 	}
+	free(text);
 	return T;
 }
 

@@ -211,6 +211,15 @@ def test_reference_tools_relinked_against_the_library(tmp_path):
                     rows.setdefault(int(p[0]), []).append((int(p[1]), int(p[2])))
             return n, m, sorted((v[0], tuple(sorted(v[1:]))) for v in rows.values())
         assert canon(a.stdout) == canon(b.stdout)
+    # rank --certificate: L mode, the three factorization checks of tools/rank.c:107-109 (asserts), certificate created,
+    # verified and saved; the saved file loads and verifies again through the library (tools/check_cert.c's calls)
+    cert = tmp_path / "cert.txt"
+    a = run("b200_rank", "--certificate", "--output", str(cert))
+    assert a.returncode == 0, a.stderr[-600:]
+    assert b"\nCORRECT certificate" in a.stderr and b"INCORRECT" not in a.stderr
+    text = cert.read_text().split("\n")
+    assert int(text[0]) == int(ra) and int(text[1]) == t.prime
+    assert len(text[3].split()) == int(ra) and len(text[6].split()) == int(ra)
 
 
 @pytest.mark.parametrize("batch", ["7", "64", "1024"])

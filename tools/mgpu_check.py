@@ -25,6 +25,7 @@ def digest(f):
     for M in (Rm.numpy(), Km.numpy()):
         for k in "pjx": h.update(np.ascontiguousarray(M[k]).tobytes())
     h.update(np.ascontiguousarray(Rqinv).tobytes())
+    digest.rref_nnz = Rm.nnz
     return f.rank, h.hexdigest()
 alone = []
 for t, o in zip(cases, opts):
@@ -41,6 +42,15 @@ for (t, o), want in zip(zip(cases, opts), alone):
     ok &= same and s.nccl_bytes > 0
     total_bytes += s.nccl_bytes
     print(f"rank {dist.get_rank()}/{dist.get_world_size()} {t.name}: rank {got[0]} identical={same} nccl_bytes={s.nccl_bytes}", flush=True)
+# gather-to-root mode (spasm_b200_comm_result_root): rank 0 holds the same result, the other ranks an empty matrix
+L.spasm_b200_comm_result_root(0)
+for (t, o), want in list(zip(zip(cases, opts), alone))[-2:]:
+    A = host.compress(L, t); oracle.reset_rand(); L.spasm_b200_reset_stats()
+    got = digest(host.echelonize(L, A, host.default_opts(L, **o)))
+    same = (got == want) if dist.get_rank() == 0 else (got[0] == want[0] and digest.rref_nnz == 0)
+    ok &= same
+    print(f"rank {dist.get_rank()}/{dist.get_world_size()} {t.name} (result on rank 0): identical={same} rref_nnz={digest.rref_nnz}", flush=True)
+L.spasm_b200_comm_result_root(-1)
 v = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(v, op=dist.ReduceOp.MIN)
 if dist.get_rank() == 0: print("MULTI-GPU PARITY", "OK" if v.item() == 1.0 else "FAILED", f"world={dist.get_world_size()} nccl_bytes_rank0={total_bytes}", flush=True)
 L.spasm_b200_comm_destroy(); dist.destroy_process_group()
