@@ -244,8 +244,10 @@ def scale_leg(L, host, spasm_b200, barrier, steps: int, scale: float, reduce_max
         L.spasm_b200_reset_stats()
         t0 = time.perf_counter()
         f = host.echelonize(L, A, o)
+        barrier()                                # a barrier after every call: each component is the time of its slowest rank
         t1 = time.perf_counter()
         Rm, _ = host.rref(L, f)
+        barrier()
         t2 = time.perf_counter()
         Km = host.kernel(L, f)
         barrier()

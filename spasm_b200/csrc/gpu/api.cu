@@ -624,7 +624,7 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv)
 	for (int j = 0; j < m; j++)
 		Rqinv[j] = -1;
 	for (int i = 0; i < n; i++)
-		Rqinv[Rm->j[Rm->p[i]]] = i;
+		Rqinv[pivcol[i]] = i;          /* the pivot of row i of R is the pivot of row i of U, emitted first (valid on the ranks that hold no rows too) */
 	spasm_human_format(spasm_nnz(Rm), hnnz);
 	LOG("[rref] done. NNZ(R) = %s\n", hnnz);
 	return Rm;
