@@ -198,6 +198,39 @@ def schur_leg(lib, host_mod, reps: int = 3):
     return len(rows), int(nnz), best
 
 
+def ingest_leg(lib) -> dict:
+    """spasm_triplet_load on the SMS text of the headline workload, entry lines parsed by the host loop and by
+    the GPU (csrc/gpu/ingest.cu); seconds include reading the file and the copy of the triplets to host memory."""
+    import tempfile
+    from spasm_b200 import synthetic
+    t = synthetic.config2(1.0)
+    text = t.to_sms()
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    out = {"workload": f"SMS text of config2: {len(text)} bytes, {len(t.i)} entries"}
+    with tempfile.NamedTemporaryFile(suffix=".sms") as tmp:
+        tmp.write(text)
+        tmp.flush()
+        for mode in ("host", "gpu"):
+            os.environ["SPASM_B200_INGEST"] = mode
+            best = None
+            for _ in range(3):
+                f = libc.fopen(tmp.name.encode(), b"r")
+                t0 = time.perf_counter()
+                T = lib.spasm_triplet_load(f, t.prime, None)
+                dt = time.perf_counter() - t0
+                libc.fclose(f)
+                assert T.contents.nz == len(t.i)
+                lib.spasm_triplet_free(T)
+                best = dt if best is None else min(best, dt)
+            out[mode + "_s"] = best
+            out[mode + "_MBps"] = len(text) / best / 1e6
+        os.environ.pop("SPASM_B200_INGEST", None)
+    return out
+
+
 def run_schur_reference() -> None:
     """the same call through oracle/_ref on all host cores (subprocess of the GPU arm, rank 0, N=1)"""
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
@@ -537,6 +570,10 @@ def main() -> None:
                 lines[0]["schur_rows_per_s"] = sch["rows_per_s"]
             except Exception as exc:     # a leg, never the headline
                 lines[0]["schur"] = {"failed": str(exc)}
+            try:
+                lines[0]["ingest"] = ingest_leg(L)
+            except Exception as exc:
+                lines[0]["ingest"] = {"failed": str(exc)}
         for line in lines:
             print(json.dumps(line), flush=True)
     if dist is not None:
