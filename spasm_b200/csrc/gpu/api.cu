@@ -219,31 +219,51 @@ static void append_L_from_panel(Engine &E, struct spasm_triplet *L, const int *r
  * pivotal ones (fact->p) otherwise -- the reference also keeps the pivotal rows only (echelonize.c:252-270).
  * reference: src/spasm_echelonize.c:606-614 (L->m = rank, spasm_compress(L), fact->complete).
  */
-void compute_L(struct spasm_lu *fact, const DevCsr &dA, bool complete)
+void compute_L(struct spasm_lu *fact, const DevCsr &dA, const struct spasm_csr *A, bool complete, int n_first_round)
 {
 	cudaStream_t s = ctx().stream;
 	const int n = dA.n, r = fact->U->n;
+	const struct spasm_csr *U = fact->U;
 	struct spasm_triplet *L = spasm_triplet_alloc(n, r, std::max<i64>(spasm_nnz(fact->U) + n, 1), dA.prime, true);
 	if (r > 0) {
-		Engine E;
-		engine_from_host(E, fact->U, fact->qinv);
+		/* The rows behind the structural pivots of the FIRST round need no solve: row k of U is row p[k] of A divided by
+		 * its pivot, so row p[k] of L is the single entry (k, pivot) (pivots.c:421-426).  On the 500k x 500k configuration
+		 * that is 494 k of the 499 k pivotal rows. */
+		std::vector<char> settled((size_t) std::max(n, 1), 0);
+		n_first_round = std::min(n_first_round, r);
+		for (int k = 0; k < n_first_round; k++) {
+			const int i = fact->p[k], j = U->j[U->p[k]];
+			spasm_ZZp pivot = 0;
+			for (i64 px = A->p[i]; px < A->p[i + 1] && pivot == 0; px++)
+				if (A->j[px] == j)
+					pivot = A->x[px];
+			if (pivot == 0)
+				errx(1, "[spasm-b200] internal: pivot (%d, %d) not found in the input (L mode)", i, j);
+			spasm_add_entry(L, i, k, pivot);
+			settled[i] = 1;
+		}
 		std::vector<int> rows;
 		if (complete) {
-			rows.resize((size_t) n);
 			for (int i = 0; i < n; i++)
-				rows[i] = i;
+				if (!settled[i])
+					rows.push_back(i);
 		} else {
-			rows.assign(fact->p, fact->p + r);
+			for (int k = n_first_round; k < r; k++)
+				rows.push_back(fact->p[k]);
 		}
-		const int cap = panel_capacity(E.m);
-		for (size_t done = 0; done < rows.size(); done += cap) {
-			const int R = (int) std::min<size_t>(cap, rows.size() - done);
-			DevBuf<int> d_rows;
-			d_rows.upload(rows.data() + done, (size_t) R, s);
-			E.solve_rows(dA, d_rows.ptr, R, false);
-			if (panel_count_nonzero(E.panel, E.Uqinv.ptr) != 0)
-				errx(1, "[spasm-b200] internal: a row of the input is not in the span of the echelon form (L mode)");
-			append_L_from_panel(E, L, rows.data() + done, R);
+		if (!rows.empty()) {
+			Engine E;
+			engine_from_host(E, fact->U, fact->qinv);
+			const int cap = panel_capacity(E.m);
+			for (size_t done = 0; done < rows.size(); done += cap) {
+				const int R = (int) std::min<size_t>(cap, rows.size() - done);
+				DevBuf<int> d_rows;
+				d_rows.upload(rows.data() + done, (size_t) R, s);
+				E.solve_rows(dA, d_rows.ptr, R, false);
+				if (panel_count_nonzero(E.panel, E.Uqinv.ptr) != 0)
+					errx(1, "[spasm-b200] internal: a row of the input is not in the span of the echelon form (L mode)");
+				append_L_from_panel(E, L, rows.data() + done, R);
+			}
 		}
 	}
 	LOG("[echelonize] L : %" PRId64 " entries\n", L->nz);

@@ -293,7 +293,7 @@ void schur_sparse(Engine &E, const DevCsr &A, const int *p, int n, DevCsr &S, co
 }
 
 void prng_combo_coefficients(i64 prime, int N, int w, i32 *d_coef);     /* prng.cu */
-void compute_L(struct spasm_lu *fact, const DevCsr &dA, bool complete);    /* api.cu */
+void compute_L(struct spasm_lu *fact, const DevCsr &dA, const struct spasm_csr *A, bool complete, int n_first_round);    /* api.cu */
 
 /* ------------------------------------------------------------------ finishing strategies */
 
@@ -1283,6 +1283,8 @@ static void echelonize_core(Engine &E, const DevCsr &dA0, struct echelonize_opts
 		}
 		LOG("[echelonize] round %d\n", round);
 		npiv = extract_structural(E, *cur, p_in.empty() ? NULL : p_in.data(), p.data(), opts->enable_greedy_pivot_search, round, true);
+		if (round == 0)
+			E.first_round_rows = npiv;       /* rows 0 .. npiv-1 of U: one scaled row of the INPUT each (compute_L) */
 		lap("extract_structural");
 		st.pub.nrounds = round + 1;
 		st.pair_start.push_back((int) st.pair_row.size());
@@ -1426,7 +1428,7 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
 	}
 	struct spasm_lu *fact = assemble(E, 0);
 	if (opts->L)
-		compute_L(fact, dA0, opts->complete != 0);
+		compute_L(fact, dA0, A, opts->complete != 0, E.first_round_rows);
 	stats().pub.ms_device_echelonize = timer.stop_ms();
 	stats().pub.ms_total_echelonize = 1e3 * (spasm_wtime() - start);
 	LOG("[echelonize] Done in %.3fs. Rank %d, %" PRId64 " nz in basis\n", spasm_wtime() - start, fact->U->n, spasm_nnz(fact->U));

@@ -24,6 +24,7 @@ void Engine::init(int m_, i64 prime_)
 	dense_rank = 0;
 	Sm0 = 0;
 	want_L = false;
+	first_round_rows = 0;
 	p_struct.clear();
 	p_dense.clear();
 }

@@ -40,6 +40,7 @@ struct Engine {
 	int lazy_rows = 0;               /* the first lazy_rows rows of U are in column order: assemble() puts them in level order */
 	/* L mode (opts->L): row of the input matrix each row of the echelon form was obtained from (fact->p) */
 	bool want_L = false;
+	int first_round_rows = 0;        /* structural pivots of round 0 (rows 0 .. first_round_rows-1 of U, in any order) */
 	std::vector<int> p_struct;       /* per row of U */
 	std::vector<int> p_dense;        /* per dense row, block after block */
 	/* dense part, over the columns that are non-pivotal after the structural rounds */
