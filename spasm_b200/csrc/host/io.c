@@ -123,6 +123,8 @@ i64 spasm_b200_ingest_entries(const char *text, size_t bytes, struct spasm_tripl
  * working without a GPU. */
 static bool ingest_on_gpu(size_t bytes)
 {
+	if (bytes >= ((size_t) 1 << 32))
+		return false;          /* the device pass indexes the text with 32-bit offsets: larger inputs keep the host loop */
 	const char *mode = getenv("SPASM_B200_INGEST");
 	if (mode != NULL && strcmp(mode, "host") == 0)
 		return false;
