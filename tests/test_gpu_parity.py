@@ -220,6 +220,40 @@ def test_reference_tools_relinked_against_the_library(tmp_path):
     text = cert.read_text().split("\n")
     assert int(text[0]) == int(ra) and int(text[1]) == t.prime
     assert len(text[3].split()) == int(ra) and len(text[6].split()) == int(ra)
+    # tools/solve.c relinked: X * A == B for right-hand sides in the row space (spasm_echelonize with L + spasm_gesv)
+    if os.path.exists(os.path.join(here, "b200_solve")):
+        rng = np.random.default_rng(5)
+        At = {}
+        for i, j, x in zip(t.i.tolist(), t.j.tolist(), t.x.tolist()):
+            At.setdefault(i, {})
+            At[i][j] = (At[i].get(j, 0) + x) % t.prime
+        nb = 4
+        combos = [{int(r): int(c) for r, c in zip(rng.integers(0, t.n, 5), rng.integers(1, t.prime, 5))} for _ in range(nb)]
+        rhs_rows = []
+        for comb in combos:
+            acc = {}
+            for r, c in comb.items():
+                for j, x in At.get(r, {}).items():
+                    acc[j] = (acc.get(j, 0) + c * x) % t.prime
+            rhs_rows.append(acc)
+        rhs = tmp_path / "rhs.sms"
+        with open(rhs, "w") as f:
+            f.write(f"{nb} {t.m} M\n")
+            for k, acc in enumerate(rhs_rows):
+                for j, x in acc.items():
+                    if x:
+                        f.write(f"{k + 1} {j + 1} {x}\n")
+            f.write("0 0 0\n")
+        xs = tmp_path / "x.sms"
+        a = run("b200_solve", "--rhs", str(rhs), "--output", str(xs))
+        assert a.returncode == 0 and b"no solution" not in a.stderr, a.stderr[-600:]
+        X = util.load_sms(str(xs), t.prime)
+        for k in range(nb):
+            acc = {}
+            for i, c in zip(X.j[X.i == k].tolist(), X.x[X.i == k].tolist()):
+                for j, x in At.get(i, {}).items():
+                    acc[j] = (acc.get(j, 0) + c * x) % t.prime
+            assert {j: v for j, v in acc.items() if v} == {j: v for j, v in rhs_rows[k].items() if v}
 
 
 @pytest.mark.parametrize("batch", ["7", "64", "1024"])
