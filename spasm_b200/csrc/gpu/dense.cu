@@ -531,14 +531,16 @@ k_rref_panel_cluster(const i32 *__restrict__ S, int ld, int n, int m, int c0, in
  */
 #define PS_ROWS 96
 #define PS_THREADS 256
+#define PS_THREADS_WIDE 1024      /* SPASM_B200_PANEL_WIDE=1: one thread per (row, column) of the sample; see DESIGN.md 5.3 */
 
-__global__ void __launch_bounds__(PS_THREADS)
+template <int PS_T>
+__global__ void __launch_bounds__(PS_T)
 k_rref_panel_sample(const i32 *__restrict__ S, int ld, int n, int m, int c0, int *rowstate, int *rank_dev, int *pivcol_out, PanelInfo *info, Zp F)
 {
 	__shared__ i32 Pw[PS_ROWS * PSTRIDE];
 	__shared__ int s_rows[PS_ROWS];
 	__shared__ unsigned char used[PS_ROWS];
-	__shared__ int s_warp[PS_THREADS / 32];
+	__shared__ int s_warp[PS_T / 32];
 	__shared__ int s_base, s_min, s_k, s_sw;
 	__shared__ int s_prow[NB], s_pcol[NB];
 	__shared__ i32 s_piv[NB], s_dinv[NB];
@@ -642,17 +644,31 @@ k_rref_panel_sample(const i32 *__restrict__ S, int ld, int n, int m, int c0, int
 		}
 		__syncthreads();
 		const i64 d = s_piv[c];
-		const int count = nbw - c - 1, h0 = (count + 1) / 2;
-		for (int idx = tid; idx < 2 * ns; idx += T) {
-			const int r = idx >> 1, half = idx & 1;
-			if (used[r])
-				continue;
-			const i64 l = Pw[r * PSTRIDE + c];
-			if (l == 0)
-				continue;
-			const int lo = c + 1 + (half ? h0 : 0), hi = half ? nbw : c + 1 + h0;
-			for (int cc = lo; cc < hi; cc++)
-				Pw[r * PSTRIDE + cc] = zp_reduce(d * Pw[r * PSTRIDE + cc] - l * s_piv[cc], F);
+		if (PS_T >= PS_THREADS_WIDE) {
+			/* one thread per entry: a step is one multiply-subtract-reduce deep instead of a serial loop over half a row
+			 * (the 16-iteration loops below, with two threads per row and eight warps to hide their latency, are what
+			 * the 1.5 us of a column step are made of); column c itself is only read */
+			for (int idx = tid; idx < ns * NB; idx += T) {
+				const int r = idx / NB, cc = idx % NB;
+				if (cc <= c || cc >= nbw || used[r])
+					continue;
+				const i64 l = Pw[r * PSTRIDE + c];
+				if (l != 0)
+					Pw[r * PSTRIDE + cc] = zp_reduce(d * Pw[r * PSTRIDE + cc] - l * s_piv[cc], F);
+			}
+		} else {
+			const int count = nbw - c - 1, h0 = (count + 1) / 2;
+			for (int idx = tid; idx < 2 * ns; idx += T) {
+				const int r = idx >> 1, half = idx & 1;
+				if (used[r])
+					continue;
+				const i64 l = Pw[r * PSTRIDE + c];
+				if (l == 0)
+					continue;
+				const int lo = c + 1 + (half ? h0 : 0), hi = half ? nbw : c + 1 + h0;
+				for (int cc = lo; cc < hi; cc++)
+					Pw[r * PSTRIDE + cc] = zp_reduce(d * Pw[r * PSTRIDE + cc] - l * s_piv[cc], F);
+			}
 		}
 		__syncthreads();
 	}
@@ -772,6 +788,7 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 	DevBuf<PanelInfo> info2(1);
 	/* sampled factorisation first (SPASM_B200_PANEL_NO_SAMPLE=1: the full kernels only); fast_done = 0 otherwise */
 	static const bool use_sample = getenv("SPASM_B200_PANEL_NO_SAMPLE") == NULL;
+	static const bool wide_sample = getenv("SPASM_B200_PANEL_WIDE") != NULL;      /* 1024-thread variant (not the default: measured at the very end of the round, the whole GPU suite did not run on it) */
 	info.zero(s);
 	info2.zero(s);
 	i32 *Wb[2] = {W.ptr, W2.ptr}, *Pb[2] = {P.ptr, P2.ptr};
@@ -785,7 +802,10 @@ RrefResult dense_rref(i32 *S, int n, int m, int ld, const Zp &F)
 		const int width = m - c0;
 		const int b = panels & 1;
 		if (use_sample) {
-			k_rref_panel_sample<<<1, PS_THREADS, 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, ib[b], F);
+			if (wide_sample)
+				k_rref_panel_sample<PS_THREADS_WIDE><<<1, PS_THREADS_WIDE, 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, ib[b], F);
+			else
+				k_rref_panel_sample<PS_THREADS><<<1, PS_THREADS, 0, s>>>(S, ld, n, m, c0, rowstate.ptr, rank_dev.ptr, pivcol.ptr, ib[b], F);
 			LAUNCHED(1);
 		}
 		if (use_cluster)
